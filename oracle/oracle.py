@@ -1,0 +1,327 @@
+"""CPU oracle for the rulebook -> gather-GEMM-scatter hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product package
+(``spconv_b200``) never does.  Parity status is "unpinned for pair ORDER" in the
+reference's own tests (see the header of ``spconv_oracle.c``); rulebook CONTENT and the
+conv arithmetic are pinned by the reference's dense-convolution equivalence test, which
+``tests/test_oracle.py`` reruns on CPU.
+
+What is restated (paths relative to /root/reference):
+
+* rulebooks ............ ``spconv_oracle.c`` (C, compiled with gcc by :func:`build`)
+* buffer shapes / fill .. ``spconv/csrc/sparse/all.py:2064-2127`` (``get_indice_pairs``)
+* "points vanished" .... ``spconv/pytorch/ops.py:54-70,260-262``
+* CPU conv fwd ......... ``spconv/csrc/sparse/convops.py:1534-1633`` + mm callbacks
+                         ``spconv/pytorch/cppcore.py:232-262`` (``buf @ W_k^T``)
+* CPU conv bwd ......... ``spconv/csrc/sparse/convops.py:1769-1860`` + ``cppcore.py:290-348``
+* SubM mirror rule ..... ``spconv/pytorch/ops.py:962-968`` (``nhot = num[kv-1-k]``)
+* implicit-GEMM tables . derived (the reference builds them on GPU only,
+                         ``spconv/csrc/sparse/indices.py:807-874,600-721``); SURVEY A.5
+* int8 epilogue ........ ``test/test_all_algo.py:272-287``
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "spconv_oracle.c")
+_LIB = os.path.join(_HERE, "_build", "libspconv_oracle.so")
+_lib: Optional[ctypes.CDLL] = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (seconds)."""
+    if (not force and os.path.exists(_LIB)
+            and os.path.getmtime(_LIB) >= os.path.getmtime(_SRC)):
+        return _LIB
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-o", _LIB, _SRC]
+    subprocess.run(cmd, check=True)
+    return _LIB
+
+
+def _load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
+            try:
+                build()
+            except Exception:
+                if not os.path.exists(_LIB):
+                    raise
+        _lib = ctypes.CDLL(_LIB)
+        _lib.orc_subm_rulebook.restype = ctypes.c_int
+        _lib.orc_conv_rulebook.restype = ctypes.c_int
+    return _lib
+
+
+def _iarr(v: Sequence[int]):
+    return (ctypes.c_int * len(v))(*[int(x) for x in v])
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def get_conv_output_size(input_size, kernel_size, stride, padding, dilation) -> List[int]:
+    out = []
+    for i in range(len(input_size)):
+        if kernel_size[i] == -1:
+            out.append(1)
+        else:
+            out.append((input_size[i] + 2 * padding[i] - dilation[i] * (kernel_size[i] - 1) - 1)
+                       // stride[i] + 1)
+    return out
+
+
+def get_deconv_output_size(input_size, kernel_size, stride, padding, dilation,
+                           output_padding) -> List[int]:
+    out = []
+    for i in range(len(input_size)):
+        if kernel_size[i] == -1:
+            raise ValueError("deconv don't support kernel_size < 0")
+        out.append((input_size[i] - 1) * stride[i] - 2 * padding[i] + kernel_size[i]
+                   + output_padding[i])
+    return out
+
+
+def get_indice_pairs(indices: np.ndarray, batch_size: int, spatial_shape: Sequence[int],
+                     ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
+                     dilation: Sequence[int], out_padding: Sequence[int], subm: bool = False,
+                     transpose: bool = False
+                     ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Native rulebook in the reference's CPU order.
+
+    Returns ``(out_inds [M, ndim+1], pairs [2, kv, N], indice_num_per_loc [kv])`` exactly
+    as ``ops.get_indice_pairs`` does on a CPU tensor (``ops.py:132-170``).
+    """
+    lib = _load()
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    n, ndim = indices.shape[0], indices.shape[1] - 1
+    kv = int(np.prod(ksize))
+    if not subm:
+        if transpose:
+            out_shape = get_deconv_output_size(spatial_shape, ksize, stride, padding, dilation,
+                                               out_padding)
+        else:
+            out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+    else:
+        out_shape = list(spatial_shape)
+    if any(x == 0 for x in out_shape):
+        raise ValueError(
+            f"your out spatial shape {out_shape} reach zero!!! input shape: {spatial_shape}")
+    pairs = np.full((2, kv, n), -1, dtype=np.int32)
+    num = np.zeros((kv,), dtype=np.int32)
+    if subm:
+        ret = lib.orc_subm_rulebook(_ptr(indices), n, ndim, int(batch_size), _iarr(spatial_shape),
+                                    _iarr(ksize), _iarr(dilation), _ptr(pairs), _ptr(num))
+        if ret == -2:
+            raise RuntimeError("subm only support odd ksize")
+        if ret < 0:
+            raise RuntimeError(f"oracle subm rulebook failed ({ret})")
+        return indices, pairs, num
+    out_inds = np.empty((max(kv * n, 1), ndim + 1), dtype=np.int32)
+    num_act = lib.orc_conv_rulebook(_ptr(indices), n, ndim, int(batch_size), _iarr(out_shape),
+                                    _iarr(spatial_shape), _iarr(ksize), _iarr(stride),
+                                    _iarr(padding), _iarr(dilation), int(bool(transpose)),
+                                    _ptr(pairs), _ptr(out_inds), _ptr(num))
+    if num_act < 0:
+        raise RuntimeError(f"oracle conv rulebook failed ({num_act})")
+    if num_act == 0:
+        raise ValueError("Your points vanished here, this usually because you provide "
+                         "conv params that may ignore some input points. Example: "
+                         "spatial_shape=[8, 200, 200] -> stride=2 conv")
+    return out_inds[:num_act].copy(), pairs, num
+
+
+def _pair_counts(num: np.ndarray, kv: int, n_in: int, subm: bool) -> np.ndarray:
+    """valid length of pairs[:, k, :] for every k (SubM mirror rule, ops.py:962-968)."""
+    cnt = np.array(num, dtype=np.int64).copy()
+    if subm:
+        for k in range(kv):
+            if k > kv // 2:
+                cnt[k] = num[kv - 1 - k]
+            elif k == kv // 2:
+                cnt[k] = n_in
+    return cnt
+
+
+def implicit_gemm_tables(pairs: np.ndarray, num: np.ndarray, n_in: int, n_out: int, subm: bool,
+                         do_sort: bool = True):
+    """Derive the masked-implicit-GEMM artefacts from a native rulebook.
+
+    ``pair_fwd[k, o] = i``, ``pair_bwd[k, i] = o`` (-1 = none); ``mask_*`` has bit ``k % 32``
+    of word ``k // 32`` set iff the entry exists; ``argsort_*`` is the STABLE ascending
+    argsort of the masks and the returned masks are in sorted order, as
+    ``thrust::sort_by_key`` leaves them (``all.py:935-1000`` sorts keys in place).
+    """
+    kv = pairs.shape[1]
+    words = (kv + 31) // 32
+    cnt = _pair_counts(num, kv, n_in, subm)
+    pair_fwd = np.full((kv, n_out), -1, dtype=np.int32)
+    pair_bwd = np.full((kv, n_in), -1, dtype=np.int32)
+    mask_fwd = np.zeros((n_out, words), dtype=np.uint32)
+    mask_bwd = np.zeros((n_in, words), dtype=np.uint32)
+    for k in range(kv):
+        i_inds = pairs[0, k, :cnt[k]]
+        o_inds = pairs[1, k, :cnt[k]]
+        pair_fwd[k, o_inds] = i_inds
+        pair_bwd[k, i_inds] = o_inds
+        bit = np.uint32(1 << (k % 32))
+        mask_fwd[o_inds, k // 32] |= bit
+        mask_bwd[i_inds, k // 32] |= bit
+
+    def sort_masks(mask):
+        n = mask.shape[0]
+        if not do_sort:
+            return mask.copy(), np.arange(n, dtype=np.int32)
+        # thrust tuple compare: word 0 is the most significant key
+        order = np.arange(n)
+        for w in range(words - 1, -1, -1):
+            order = order[np.argsort(mask[order, w], kind="stable")]
+        return mask[order].copy(), order.astype(np.int32)
+
+    mask_fwd_sorted, argsort_fwd = sort_masks(mask_fwd)
+    mask_bwd_sorted, argsort_bwd = sort_masks(mask_bwd)
+    return {
+        "pair_fwd": pair_fwd, "pair_bwd": pair_bwd,
+        "mask_fwd_unsorted": mask_fwd, "mask_bwd_unsorted": mask_bwd,
+        "mask_fwd": mask_fwd_sorted, "mask_bwd": mask_bwd_sorted,
+        "argsort_fwd": argsort_fwd, "argsort_bwd": argsort_bwd,
+    }
+
+
+def indice_conv(features: np.ndarray, filters: np.ndarray, pairs: np.ndarray, num: np.ndarray,
+                num_activate_out: int, inverse: bool = False, subm: bool = False,
+                bias: Optional[np.ndarray] = None, act: Optional[str] = None,
+                act_alpha: float = 0.0) -> np.ndarray:
+    """fp32 gather -> mm -> scatter-add forward (``convops.py:1534-1633``).
+
+    ``filters`` is KRSC ``[K, *ksize, C]``; it is viewed ``[K, kv, C]`` and offset ``k`` uses
+    ``W_k = filters[:, k, :]`` with ``out[pair_out] += x[pair_in] @ W_k^T``.
+    """
+    x = np.asarray(features, dtype=np.float32)
+    K, C = filters.shape[0], filters.shape[-1]
+    w = np.asarray(filters, dtype=np.float32).reshape(K, -1, C)
+    kv = w.shape[1]
+    cnt = _pair_counts(num, kv, x.shape[0], subm)
+    if subm:
+        out = x @ w[:, kv // 2].T                     # cppcore.py:244-246
+    else:
+        out = np.zeros((num_activate_out, K), dtype=np.float32)
+    pin, pout = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])  # convops.py:1604-1605
+    for k in range(kv):
+        if subm and k == kv // 2:
+            continue
+        n = int(cnt[k])
+        if n <= 0:
+            continue
+        buf = x[pin[k, :n]] @ w[:, k].T
+        np.add.at(out, pout[k, :n], buf)
+    if bias is not None:
+        out = out + np.asarray(bias, dtype=np.float32)
+    return apply_act(out, act, act_alpha)
+
+
+def indice_conv_backward(features: np.ndarray, filters: np.ndarray, out_bp: np.ndarray,
+                         pairs: np.ndarray, num: np.ndarray, inverse: bool = False,
+                         subm: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """fp32 backward (``convops.py:1769-1860``): ``dW_k = dout[po]^T @ x[pi]``,
+    ``din[pi] += dout[po] @ W_k``.  Returns ``(din [N,C], dfilters KRSC)``."""
+    x = np.asarray(features, dtype=np.float32)
+    dout = np.asarray(out_bp, dtype=np.float32)
+    K, C = filters.shape[0], filters.shape[-1]
+    w = np.asarray(filters, dtype=np.float32).reshape(K, -1, C)
+    kv = w.shape[1]
+    cnt = _pair_counts(num, kv, x.shape[0], subm)
+    dw = np.zeros_like(w)
+    if subm:
+        dw[:, kv // 2] = dout.T @ x                   # cppcore.py:314-317
+        din = dout @ w[:, kv // 2]
+    else:
+        din = np.zeros_like(x)
+    pin, pout = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])
+    for k in range(kv):
+        if subm and k == kv // 2:
+            continue
+        n = int(cnt[k])
+        if n <= 0:
+            continue
+        og = dout[pout[k, :n]]
+        ig = x[pin[k, :n]]
+        dw[:, k] = og.T @ ig
+        np.add.at(din, pin[k, :n], og @ w[:, k])
+    return din, dw.reshape(filters.shape)
+
+
+def apply_act(x: np.ndarray, act: Optional[str], alpha: float = 0.0) -> np.ndarray:
+    """``inference.py:26-146`` activations: ReLU, LeakyReLU(alpha), Sigmoid."""
+    if act is None or act == "none":
+        return x
+    if act == "relu":
+        return np.maximum(x, 0)
+    if act == "leaky_relu":
+        return np.where(x >= 0, x, x * np.float32(alpha))
+    if act == "sigmoid":
+        return (1.0 / (1.0 + np.exp(-x))).astype(x.dtype)
+    raise NotImplementedError(act)
+
+
+def int8_conv_forward(features_i8: np.ndarray, filters_i8: np.ndarray, pairs, num,
+                      num_activate_out: int, subm: bool, scales: np.ndarray, bias: np.ndarray,
+                      output_add: Optional[np.ndarray] = None, output_add_scale: float = 0.0,
+                      relu: bool = False, out_int8: bool = True) -> np.ndarray:
+    """int8 inference formula of ``test/test_all_algo.py:222-287``: int32 accumulate, then
+    ``clip(round(acc * scale[k] + bias[k] + add * add_scale))`` (numpy round-half-even)."""
+    x = features_i8.astype(np.int32)
+    K, C = filters_i8.shape[0], filters_i8.shape[-1]
+    w = filters_i8.reshape(K, -1, C).astype(np.int32)
+    kv = w.shape[1]
+    cnt = _pair_counts(num, kv, x.shape[0], subm)
+    acc = np.zeros((num_activate_out, K), dtype=np.int32)
+    for k in range(kv):
+        n = int(cnt[k])
+        if n <= 0:
+            continue
+        np.add.at(acc, pairs[1][k, :n], x[pairs[0][k, :n]] @ w[:, k].T)
+    res = acc.astype(np.float32) * scales.astype(np.float32) + bias.astype(np.float32)
+    if output_add is not None:
+        res = res + output_add.astype(np.float32) * np.float32(output_add_scale)
+    if relu:
+        res = np.maximum(res, 0)
+    if out_int8:
+        return np.clip(np.round(res), -128, 127).astype(np.int8)
+    return res
+
+
+def dense_from_sparse(features: np.ndarray, indices: np.ndarray, spatial_shape, batch_size):
+    """NC(D..) dense tensor from a sparse one (``spconv/pytorch/core.py:264-275``)."""
+    C = features.shape[1]
+    dense = np.zeros((batch_size, *spatial_shape, C), dtype=features.dtype)
+    dense[tuple(indices[:, i] for i in range(indices.shape[1]))] = features
+    nd = len(spatial_shape)
+    return np.ascontiguousarray(dense.transpose(0, nd + 1, *range(1, nd + 1)))
+
+
+def generate_sparse_data(shape, num_points, num_channels, rng: np.random.Generator,
+                         data_range=(-1, 1), dtype=np.float32):
+    """Semantics of ``spconv/test_utils.py:142-195``: unique uniform-random coordinates per
+    batch sample (shuffle of the full mesh grid), uniform features."""
+    ndim = len(shape)
+    total = int(np.prod(shape))
+    inds = []
+    for b, n in enumerate(num_points):
+        flat = rng.permutation(total)[:n]
+        coords = np.stack(np.unravel_index(flat, shape), axis=-1).astype(np.int32)
+        inds.append(np.concatenate([np.full((n, 1), b, dtype=np.int32), coords], axis=1))
+    indices = np.concatenate(inds, axis=0)
+    feats = rng.uniform(data_range[0], data_range[1],
+                        size=(indices.shape[0], num_channels)).astype(dtype)
+    assert indices.shape[1] == ndim + 1
+    return feats, indices
