@@ -1,0 +1,210 @@
+/*
+ * spconv_b200.h -- C ABI of the B200-native sparse-convolution hot path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a cudaStream_t; no torch /
+ * tv::Tensor types.  Every entry point replaces one pybind entry of the reference's
+ * generated `core_cc` module (paths relative to the reference tree):
+ *
+ *   spx_subm_rulebook / spx_conv_rulebook_stage1+2 / spx_native_pairs
+ *        <- SpconvOps.get_indice_pairs              spconv/csrc/sparse/all.py:2020-2218
+ *        <- SpconvOps.get_indice_pairs_implicit_gemm spconv/csrc/sparse/all.py:1660-2016
+ *           (kernels spconv/csrc/sparse/indices.py:292-939)
+ *   spx_mask_argsort
+ *        <- SpconvOps.sort_1d_by_key_allocator[_v2]  spconv/csrc/sparse/all.py:935-1134
+ *   spx_rulebook_workspace_size
+ *        <- SpconvOps.get_indice_gen_workspace_size  spconv/csrc/sparse/all.py:1582-1656
+ *   spx_implicit_gemm_fwd
+ *        <- ConvGemmOps.implicit_gemm                spconv/csrc/sparse/convops.py:2075-2243
+ *   spx_implicit_gemm_dgrad / spx_implicit_gemm_wgrad
+ *        <- ConvGemmOps.implicit_gemm_backward       spconv/csrc/sparse/convops.py:2247-2440
+ *   spx_pairs_to_table (+ the three above)
+ *        <- ConvGemmOps.indice_conv / indice_conv_backward
+ *                                                    spconv/csrc/sparse/convops.py:1504-2071
+ *   spx_bias_act_inplace
+ *        <- InferenceOps.bias_add_act_inplace        spconv/csrc/sparse/inference.py:166-252
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - every function returns 0 on success, non-zero on failure; spx_last_error() gives the
+ *     message of the last failure on the calling thread (reference: C++ exception text);
+ *   - nothing allocates: outputs and scratch are caller-provided (the reference routes all
+ *     allocations through ExternalAllocator callbacks, spconv/csrc/sparse/alloc.py:38-123);
+ *   - all launches go to `stream`; no function synchronises the stream except
+ *     spx_conv_rulebook_stage1, which must return the data-dependent output count
+ *     (the reference syncs at the same point, spconv/csrc/sparse/indices.py:1454-1455).
+ */
+#ifndef SPCONV_B200_H_
+#define SPCONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_MAX_NDIM 4
+
+/* element types of features / filters */
+enum spx_dtype { SPX_F32 = 0, SPX_F16 = 1, SPX_BF16 = 2, SPX_I8 = 3 };
+/* tv::gemm::Activation as used by the reference epilogues */
+enum spx_act { SPX_ACT_NONE = 0, SPX_ACT_RELU = 1, SPX_ACT_SIGMOID = 2, SPX_ACT_LEAKY_RELU = 3 };
+/* how fp32 features are multiplied: exact fp32 FMA, or TF32 tensor cores
+ * (reference: SPCONV_ALLOW_TF32, spconv/constants.py:117) */
+enum spx_f32_mode { SPX_F32_EXACT = 0, SPX_F32_TF32 = 1 };
+
+typedef void *spx_stream_t; /* cudaStream_t */
+
+const char *spx_last_error(void);
+int spx_version(void);
+/* 0 if device `dev` is usable by this library (compute capability 10.x); fills sm count */
+int spx_device_check(int dev, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------ rulebook */
+
+typedef struct {
+    int ndim;                       /* 1..4 */
+    int batch_size;
+    int in_dims[SPX_MAX_NDIM];      /* input spatial shape */
+    int out_dims[SPX_MAX_NDIM];     /* output spatial shape (== in_dims for SubM) */
+    int ksize[SPX_MAX_NDIM];
+    int stride[SPX_MAX_NDIM];
+    int padding[SPX_MAX_NDIM];
+    int dilation[SPX_MAX_NDIM];
+    int transposed;                 /* regular conv only */
+} spx_conv_geometry;
+
+/* scratch bytes needed by the rulebook entry points for `num_in` inputs
+ * (`max_out` = upper bound on outputs; ignored for SubM) */
+size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_t num_in, int64_t max_out,
+                                   int is_subm);
+/* upper bound on active outputs of a regular conv (reference: get_handcrafted_max_act_out,
+ * spconv/csrc/sparse/all.py:1559-1580) */
+int64_t spx_conv_max_out(const spx_conv_geometry *g, int64_t num_in);
+
+/*
+ * SubM rulebook.  indices [N, ndim+1] int32 (b, d0, d1, ..).  Writes every element of
+ *   pair_fwd [kv, N]   pair_fwd[k][o] = i  (-1 = none)
+ *   pair_bwd [kv, N]   pair_bwd[k][i] = o  (may be NULL)
+ *   mask     [N, words] uint32, bit k%32 of word k/32 set iff pair_fwd[k][o] != -1  (may be NULL)
+ * `words` = ceil(kv/32).
+ */
+int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                      int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask,
+                      void *workspace, size_t workspace_bytes, spx_stream_t stream);
+
+/*
+ * Regular / transposed conv rulebook, two-phase because the output count M is
+ * data-dependent.  Stage 1 hashes every (offset, input) hit, ranks the distinct outputs in
+ * the reference CPU's first-touch order and returns M (host sync).  Stage 2 fills
+ *   out_inds [M, ndim+1], pair_fwd [kv, M], pair_bwd [kv, N],
+ *   mask_fwd [M, words], mask_bwd [N, words]   (masks may be NULL).
+ * The same workspace must be passed, untouched, to both stages.
+ */
+int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                             int64_t *num_out_host, void *workspace, size_t workspace_bytes,
+                             spx_stream_t stream);
+int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                             int64_t M, int32_t *out_inds, int32_t *pair_fwd, int32_t *pair_bwd,
+                             uint32_t *mask_fwd, uint32_t *mask_bwd, void *workspace,
+                             size_t workspace_bytes, spx_stream_t stream);
+
+/*
+ * Compact "Native" rulebook  pairs [2, kv, N] (-1 padded) + indice_pair_num [kv]  in the
+ * reference CPU order (ascending input index per offset), derived from pair_bwd [kv, N] by a
+ * stable scan.  For SubM only offsets < kv/2 are counted and their mirrors written, the centre
+ * row is the identity (spconv/csrc/sparse/indices.py:1670-1703).
+ */
+int spx_native_pairs(const int32_t *pair_bwd, int64_t N, int kv, int is_subm, int32_t *pairs,
+                     int32_t *indice_pair_num, void *workspace, size_t workspace_bytes,
+                     spx_stream_t stream);
+size_t spx_native_pairs_workspace_size(int64_t N, int kv);
+
+/*
+ * Inverse of spx_native_pairs for the ConvAlgo.Native operator path: scatter a compact
+ * rulebook into dense tables  table_fwd [kv, n_out] / table_bwd [kv, n_in]  and row masks.
+ * `inverse` swaps the roles of pairs[0] / pairs[1] (SparseInverseConv).  Any output may be NULL.
+ */
+int spx_pairs_to_table(const int32_t *pairs, const int32_t *indice_pair_num, int kv,
+                       int64_t pair_stride, int64_t n_in, int64_t n_out, int is_subm, int inverse,
+                       int32_t *table_fwd, int32_t *table_bwd, uint32_t *mask_fwd,
+                       uint32_t *mask_bwd, spx_stream_t stream);
+
+/*
+ * argsort[N] <- stable ascending argsort of mask[N, words] (word 0 most significant) and mask
+ * is left SORTED, as thrust::sort_by_key leaves it in the reference.  do_sort == 0: iota only.
+ */
+size_t spx_mask_argsort_workspace_size(int64_t N, int words);
+int spx_mask_argsort(uint32_t *mask, int32_t *argsort, int64_t N, int words, int kv, int do_sort,
+                     void *workspace, size_t workspace_bytes, spx_stream_t stream);
+
+/* ------------------------------------------------------------------ conv arithmetic */
+
+typedef struct {
+    int dtype;                  /* spx_dtype of features, filters, outputs */
+    int f32_mode;               /* spx_f32_mode, only read when dtype == SPX_F32 */
+    int kv;                     /* kernel volume */
+    int c_in, c_out;            /* C, K of the KRSC filter [K, kv, C] */
+    int64_t n_in, n_out;        /* rows of the input / output feature matrices */
+    const int32_t *pair;        /* [kv, rows] gather table of THIS pass (see each function) */
+    int64_t pair_stride;        /* elements between consecutive offsets of `pair` */
+    const uint32_t *mask;       /* [rows, words] in argsort order, or NULL = all offsets */
+    const int32_t *argsort;     /* [rows] row visiting order, or NULL = identity */
+    int reverse_offsets;        /* 1: offset k of `pair`/`mask` multiplies filter kv-1-k
+                                   (SubM dgrad through the forward table; reference
+                                   reverse_mask, spconv/csrc/sparse/convops.py:2412) */
+} spx_gemm_desc;
+
+/*
+ * out[o, :] = act( sum_k x[pair[k][o], :] @ W[:, k, :]^T  + bias )      rows = n_out
+ * filters: KRSC [c_out, kv, c_in].  bias (same dtype as features) may be NULL.
+ * mask_out [ceil(n_out/128), words] (may be NULL) receives the per-128-row-tile OR of `mask`
+ * (the reference's mask_output_fwd, mask_width = 128).
+ */
+int spx_implicit_gemm_fwd(const spx_gemm_desc *d, const void *features, const void *filters,
+                          void *out, const void *bias, int act, float act_alpha,
+                          uint32_t *mask_out, spx_stream_t stream);
+
+/*
+ * din[i, :] = sum_k dout[pair[k][i], :] @ W[:, k', :]        rows = n_in, k' = k or kv-1-k
+ * `pair` is the backward table [kv, n_in] (in -> out).
+ */
+int spx_implicit_gemm_dgrad(const spx_gemm_desc *d, const void *out_bp, const void *filters,
+                            void *din, spx_stream_t stream);
+
+/*
+ * dW[:, k, :] = sum_o dout[o, :]^T  x[pair[k][o], :]          rows = n_out, pair = forward table
+ * dfilters: KRSC, same dtype as features.  workspace holds fp32 partial sums.
+ */
+size_t spx_implicit_gemm_wgrad_workspace_size(const spx_gemm_desc *d);
+int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const void *out_bp,
+                            void *dfilters, void *workspace, size_t workspace_bytes,
+                            spx_stream_t stream);
+
+/* x[r, j] = act(x[r, j] + bias[j])   in place; bias may be NULL */
+int spx_bias_act_inplace(void *x, const void *bias, int64_t rows, int cols, int dtype, int act,
+                         float act_alpha, spx_stream_t stream);
+
+/*
+ * int8 inference forward (reference formula: test/test_all_algo.py:272-287,
+ * spconv/pytorch/quantization/quantized/conv.py:368-377):
+ *   acc_i32 = sum_k x_i8[pair[k][o]] @ W_i8[:, k, :]^T
+ *   y = acc * scale[j] + bias[j] (+ add_i8[o, j] * add_scale);  act;  q = clip(rint(y), -128, 127)
+ * out_dtype: SPX_I8 (quantised) or SPX_F32 / SPX_F16 (y stored directly).
+ */
+int spx_implicit_gemm_fwd_int8(const spx_gemm_desc *d, const int8_t *features,
+                               const int8_t *filters, void *out, int out_dtype,
+                               const float *scale, const float *bias, const int8_t *output_add,
+                               float output_add_scale, int act, float act_alpha,
+                               spx_stream_t stream);
+
+/* which kernel family served the last call of each kind on this thread: 0 none, 1 SIMT,
+ * 2 tcgen05.  Used by tests/bench to prove the tensor-core path ran. */
+int spx_last_kernel_family(void);
+/* number of kernel launches issued by this library on the calling thread since the last reset */
+int64_t spx_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCONV_B200_H_ */

@@ -1,0 +1,797 @@
+// Rulebook (indice-pair) generation for SubM and regular/transposed sparse convolution.
+//
+// Replaces the reference's hash + atomic-append kernels (spconv/csrc/sparse/indices.py:292-939)
+// and their host drivers (spconv/csrc/sparse/all.py:1660-2218).  Design differences, on purpose:
+//   * one packed 64-bit slot {key:32 | value:32} per hash entry so a probe is ONE 8-byte load
+//     (the reference probes split key/value arrays: "performance bound", indices.py:791);
+//   * the dense tables pair_fwd / pair_bwd are written exactly once, coalesced, -1 included
+//     (no torch.full(-1) pre-pass + scattered writes);
+//   * every ordering decision is deterministic and equal to the reference *CPU* rulebook
+//     (indices.py:1640-1778): outputs of a regular conv are ranked by first touch in
+//     offset-major order (atomicMin of k*N+i, then a radix sort of the minima), compact
+//     "Native" pairs come from a stable per-offset scan instead of atomicAggInc.
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace spx {
+
+// ------------------------------------------------------------------ geometry
+struct Geom {
+    int ndim, batch, kv;
+    int in_dims[SPX_MAX_NDIM], out_dims[SPX_MAX_NDIM], ksize[SPX_MAX_NDIM];
+    int stride[SPX_MAX_NDIM], padding[SPX_MAX_NDIM], dilation[SPX_MAX_NDIM];
+    int transposed;
+};
+
+static Geom make_geom(const spx_conv_geometry *g, bool subm) {
+    Geom r;
+    memset(&r, 0, sizeof(r));
+    r.ndim = g->ndim;
+    r.batch = g->batch_size;
+    r.kv = 1;
+    r.transposed = g->transposed;
+    for (int a = 0; a < g->ndim; ++a) {
+        r.in_dims[a] = g->in_dims[a];
+        r.ksize[a] = g->ksize[a];
+        r.dilation[a] = g->dilation[a];
+        r.kv *= g->ksize[a];
+        if (subm) {  // indices.py:1648-1657: stride 1, pad = (k/2)*dil, out dims = in dims
+            r.out_dims[a] = g->in_dims[a];
+            r.stride[a] = 1;
+            r.padding[a] = (g->ksize[a] / 2) * g->dilation[a];
+        } else {
+            r.out_dims[a] = g->out_dims[a];
+            r.stride[a] = g->stride[a];
+            r.padding[a] = g->padding[a];
+        }
+    }
+    return r;
+}
+
+static bool needs_i64(const Geom &g, const int *dims) {
+    // same rule as the reference: int64 keys once batch * prod(dims) reaches 2^31
+    // (spconv/pytorch/ops.py:188-190, ConvProblem::check_npq_not_overflow)
+    double v = (double)g.batch;
+    for (int a = 0; a < g.ndim; ++a) v *= (double)dims[a];
+    return v >= 2147483647.0;
+}
+
+// ------------------------------------------------------------------ hash tables
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+
+// 32-bit keys: one packed slot, key in the high word so that atomicMin on the slot is a
+// min over the value for equal keys.
+struct Table32 {
+    unsigned long long *slots;
+    uint32_t cap_mask;
+    static constexpr unsigned long long EMPTY = ~0ull;
+    __device__ __forceinline__ void insert_min(int64_t key64, int32_t val) const {
+        uint32_t key = (uint32_t)key64;
+        unsigned long long packed = ((unsigned long long)key << 32) | (uint32_t)val;
+        uint32_t h = mix32(key) & cap_mask;
+        while (true) {
+            unsigned long long prev = atomicCAS(&slots[h], EMPTY, packed);
+            if (prev == EMPTY) return;
+            if ((uint32_t)(prev >> 32) == key) {
+                if ((uint32_t)prev > (uint32_t)val) atomicMin(&slots[h], packed);
+                return;
+            }
+            h = (h + 1) & cap_mask;
+        }
+    }
+    // returns slot index or -1
+    __device__ __forceinline__ int64_t find_slot(int64_t key64, int32_t &val) const {
+        uint32_t key = (uint32_t)key64;
+        uint32_t h = mix32(key) & cap_mask;
+        while (true) {
+            unsigned long long cur = __ldg(&slots[h]);
+            if (cur == EMPTY) return -1;
+            if ((uint32_t)(cur >> 32) == key) { val = (int32_t)(uint32_t)cur; return h; }
+            h = (h + 1) & cap_mask;
+        }
+    }
+    __device__ __forceinline__ bool occupied(uint32_t s, int64_t &key, int32_t &val) const {
+        unsigned long long cur = slots[s];
+        if (cur == EMPTY) return false;
+        key = (int64_t)(uint32_t)(cur >> 32);
+        val = (int32_t)(uint32_t)cur;
+        return true;
+    }
+    __device__ __forceinline__ void set_value(uint32_t s, int32_t val) const {
+        unsigned long long cur = slots[s];
+        slots[s] = (cur & 0xFFFFFFFF00000000ull) | (uint32_t)val;
+    }
+};
+
+// 64-bit keys: split arrays (volume >= 2^31)
+struct Table64 {
+    long long *keys;   // EMPTY = -1
+    int32_t *vals;     // initialised to INT_MAX
+    uint32_t cap_mask;
+    __device__ __forceinline__ void insert_min(int64_t key, int32_t val) const {
+        uint32_t h = mix64((uint64_t)key) & cap_mask;
+        while (true) {
+            long long prev = (long long)atomicCAS((unsigned long long *)&keys[h], (unsigned long long)-1ll,
+                                                  (unsigned long long)key);
+            if (prev == -1ll || prev == key) { atomicMin(&vals[h], val); return; }
+            h = (h + 1) & cap_mask;
+        }
+    }
+    __device__ __forceinline__ int64_t find_slot(int64_t key, int32_t &val) const {
+        uint32_t h = mix64((uint64_t)key) & cap_mask;
+        while (true) {
+            long long cur = keys[h];
+            if (cur == -1ll) return -1;
+            if (cur == key) { val = vals[h]; return h; }
+            h = (h + 1) & cap_mask;
+        }
+    }
+    __device__ __forceinline__ bool occupied(uint32_t s, int64_t &key, int32_t &val) const {
+        long long cur = keys[s];
+        if (cur == -1ll) return false;
+        key = cur; val = vals[s];
+        return true;
+    }
+    __device__ __forceinline__ void set_value(uint32_t s, int32_t val) const { vals[s] = val; }
+};
+
+static uint32_t table_capacity(int64_t n_items) {
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)n_items * 2) cap <<= 1;
+    return (uint32_t)cap;
+}
+
+// ------------------------------------------------------------------ coordinate helpers
+__device__ __forceinline__ void load_coord(const int32_t *indices, int64_t i, int ndim, int (&c)[SPX_MAX_NDIM + 1]) {
+    if (ndim == 3) {
+        int4 v = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+        const int32_t *p = indices + i * (ndim + 1);
+#pragma unroll
+        for (int a = 0; a <= SPX_MAX_NDIM; ++a) if (a <= ndim) c[a] = __ldg(p + a);
+    }
+}
+
+__device__ __forceinline__ int64_t linear_key(const int (&c)[SPX_MAX_NDIM + 1], const int *dims, int ndim) {
+    int64_t k = c[0];
+#pragma unroll
+    for (int a = 0; a < SPX_MAX_NDIM; ++a) if (a < ndim) k = k * dims[a] + c[a + 1];
+    return k;
+}
+
+__device__ __forceinline__ void offset_taps(int k, const int *ksize, int ndim, int (&r)[SPX_MAX_NDIM]) {
+#pragma unroll
+    for (int a = SPX_MAX_NDIM - 1; a >= 0; --a) if (a < ndim) { r[a] = k % ksize[a]; k /= ksize[a]; }
+}
+
+// ------------------------------------------------------------------ SubM
+template <typename Table>
+__global__ void subm_insert_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c[SPX_MAX_NDIM + 1];
+    load_coord(indices, i, g.ndim, c);
+    table.insert_min(linear_key(c, g.in_dims, g.ndim), (int32_t)i);
+}
+
+// one thread per voxel, all kv offsets: pair_fwd[k][o] = index of the voxel at
+// coord(o) - pad + r_k * dil (query_nhw, indices.py:222-236), coalesced writes, no atomics.
+template <typename Table>
+__global__ void subm_probe_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N,
+                                  int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
+                                  uint32_t *__restrict__ mask, int words) {
+    int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    int c[SPX_MAX_NDIM + 1];
+    load_coord(indices, o, g.ndim, c);
+    const int kv = g.kv;
+    uint32_t mword = 0;
+    int r[SPX_MAX_NDIM] = {0, 0, 0, 0};
+    for (int k = 0; k < kv; ++k) {
+        int32_t found = -1;
+        if (k == kv / 2) {
+            found = (int32_t)o;   // centre: identity (indices.py:1671-1676)
+        } else {
+            int q[SPX_MAX_NDIM + 1];
+            q[0] = c[0];
+            bool valid = c[0] >= 0 && c[0] < g.batch;
+#pragma unroll
+            for (int a = 0; a < SPX_MAX_NDIM; ++a) {
+                if (a < g.ndim) {
+                    q[a + 1] = c[a + 1] - g.padding[a] + r[a] * g.dilation[a];
+                    valid = valid && q[a + 1] >= 0 && q[a + 1] < g.in_dims[a];
+                }
+            }
+            if (valid) {
+                int32_t v;
+                if (table.find_slot(linear_key(q, g.in_dims, g.ndim), v) >= 0) found = v;
+            }
+        }
+        pair_fwd[(int64_t)k * N + o] = found;
+        if (pair_bwd) pair_bwd[(int64_t)(kv - 1 - k) * N + o] = found;
+        if (found >= 0) mword |= 1u << (k & 31);
+        if (mask && ((k & 31) == 31 || k == kv - 1)) {
+            mask[o * words + (k >> 5)] = mword;
+            mword = 0;
+        }
+        // advance taps row-major, last axis fastest (ConvOutLocIter::operator++, indices.py:117-127)
+#pragma unroll
+        for (int a = SPX_MAX_NDIM - 1; a >= 0; --a) {
+            if (a < g.ndim) {
+                if (++r[a] < g.ksize[a]) break;
+                r[a] = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ regular / transposed conv
+__device__ __forceinline__ bool conv_out_coord(const Geom &g, const int (&c)[SPX_MAX_NDIM + 1],
+                                               const int (&r)[SPX_MAX_NDIM], int (&o)[SPX_MAX_NDIM + 1]) {
+    bool valid = c[0] >= 0 && c[0] < g.batch;
+    o[0] = c[0];
+#pragma unroll
+    for (int a = 0; a < SPX_MAX_NDIM; ++a) {
+        if (a < g.ndim) {
+            if (g.transposed) {   // query_nhw_out, indices.py:253-269
+                o[a + 1] = c[a + 1] * g.stride[a] - g.padding[a] + r[a] * g.dilation[a];
+                valid = valid && o[a + 1] >= 0 && o[a + 1] < g.out_dims[a];
+            } else {              // query_npq, indices.py:141-203
+                int h = c[a + 1] + g.padding[a] - r[a] * g.dilation[a];
+                o[a + 1] = h / g.stride[a];
+                valid = valid && o[a + 1] >= 0 && o[a + 1] < g.out_dims[a] && (h % g.stride[a] == 0);
+            }
+        }
+    }
+    return valid;
+}
+
+// grid (ceil(N/T), kv): hash every hit, payload = k*N + i (first touch in offset-major order)
+template <typename Table>
+__global__ void conv_insert_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int k = blockIdx.y;
+    int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
+    load_coord(indices, i, g.ndim, c);
+    offset_taps(k, g.ksize, g.ndim, r);
+    if (conv_out_coord(g, c, r, o))
+        table.insert_min(linear_key(o, g.out_dims, g.ndim), (int32_t)((int64_t)k * N + i));
+}
+
+// compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next)
+template <typename Table>
+__global__ void conv_collect_kernel(Table table, uint32_t capacity, uint32_t *__restrict__ payload,
+                                    uint32_t *__restrict__ slot_of, int *__restrict__ counter) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = false;
+    int64_t key; int32_t val = 0;
+    if (s < capacity) occ = table.occupied(s, key, val);
+    unsigned ballot = __ballot_sync(0xffffffffu, occ);
+    if (ballot == 0) return;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (occ) {
+        int pos = base + __popc(ballot & ((1u << lane) - 1));
+        payload[pos] = (uint32_t)val;
+        slot_of[pos] = s;
+    }
+}
+
+// rank r (first-touch order) -> write r into its slot, decode the key into out_inds[r]
+template <typename Table>
+__global__ void conv_assign_kernel(Table table, Geom g, const uint32_t *__restrict__ sorted_slot, int64_t M,
+                                   int32_t *__restrict__ out_inds) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    uint32_t s = sorted_slot[r];
+    int64_t key; int32_t val;
+    table.occupied(s, key, val);
+    table.set_value(s, (int32_t)r);
+    int32_t *dst = out_inds + r * (g.ndim + 1);
+    for (int a = g.ndim - 1; a >= 0; --a) {
+        dst[a + 1] = (int32_t)(key % g.out_dims[a]);
+        key /= g.out_dims[a];
+    }
+    dst[0] = (int32_t)key;
+}
+
+// grid (ceil(N/T), kv): pair_bwd[k][i] = o (every element written), pair_fwd[k][o] = i
+template <typename Table>
+__global__ void conv_pairs_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N, int64_t M,
+                                  int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int k = blockIdx.y;
+    int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
+    load_coord(indices, i, g.ndim, c);
+    offset_taps(k, g.ksize, g.ndim, r);
+    int32_t out = -1;
+    if (conv_out_coord(g, c, r, o)) {
+        int32_t v;
+        if (table.find_slot(linear_key(o, g.out_dims, g.ndim), v) >= 0) out = v;
+    }
+    pair_bwd[(int64_t)k * N + i] = out;
+    if (out >= 0) pair_fwd[(int64_t)k * M + out] = (int32_t)i;
+}
+
+// mask[row] = bits of the non-negative entries of table[:, row]
+__global__ void table_mask_kernel(const int32_t *__restrict__ table, int64_t rows, int kv, int words,
+                                  uint32_t *__restrict__ mask) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t m = 0;
+    for (int k = 0; k < kv; ++k) {
+        if (table[(int64_t)k * rows + r] >= 0) m |= 1u << (k & 31);
+        if ((k & 31) == 31 || k == kv - 1) { mask[r * words + (k >> 5)] = m; m = 0; }
+    }
+}
+
+// ------------------------------------------------------------------ Native compact pairs (stable scan)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// rows: regular conv -> kv rows (row k of pair_bwd); SubM -> kv/2 rows
+__global__ void native_count_kernel(const int32_t *__restrict__ pair_bwd, int64_t N, int *__restrict__ block_counts,
+                                    int nblk) {
+    int row = blockIdx.y;
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        int64_t i = base + j * SCAN_THREADS + threadIdx.x;
+        if (i < N && pair_bwd[(int64_t)row * N + i] >= 0) ++cnt;
+    }
+    typedef cub::BlockReduce<int, SCAN_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    int total = BR(tmp).Sum(cnt);
+    if (threadIdx.x == 0) block_counts[row * nblk + blockIdx.x] = total;
+}
+
+// one block per row: exclusive scan of the block counts, total -> num[row]
+__global__ void native_scan_kernel(int *__restrict__ block_counts, int nblk, int32_t *__restrict__ num) {
+    int row = blockIdx.x;
+    typedef cub::BlockScan<int, SCAN_THREADS> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += SCAN_THREADS) {
+        int b = b0 + threadIdx.x;
+        int v = b < nblk ? block_counts[row * nblk + b] : 0;
+        int excl, agg;
+        BS(tmp).ExclusiveSum(v, excl, agg);
+        int carry = carry_s;
+        if (b < nblk) block_counts[row * nblk + b] = carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + agg;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) num[row] = carry_s;
+}
+
+__global__ void native_write_kernel(const int32_t *__restrict__ pair_bwd, int64_t N, int kv, int is_subm,
+                                    const int *__restrict__ block_offsets, int nblk, int32_t *__restrict__ pairs) {
+    int row = blockIdx.y;
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    // blocked arrangement keeps ascending-i order inside the tile
+    int32_t vals[SCAN_ITEMS];
+    int flags[SCAN_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        int64_t i = base + (int64_t)threadIdx.x * SCAN_ITEMS + j;
+        vals[j] = i < N ? pair_bwd[(int64_t)row * N + i] : -1;
+        flags[j] = vals[j] >= 0;
+        cnt += flags[j];
+    }
+    typedef cub::BlockScan<int, SCAN_THREADS> BS;
+    __shared__ typename BS::TempStorage tmp;
+    int excl;
+    BS(tmp).ExclusiveSum(cnt, excl);
+    int pos = block_offsets[row * nblk + blockIdx.x] + excl;
+    int32_t *pin = pairs, *pout = pairs + (int64_t)kv * N;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (flags[j]) {
+            int32_t i = (int32_t)(base + (int64_t)threadIdx.x * SCAN_ITEMS + j);
+            int32_t o = vals[j];
+            pin[(int64_t)row * N + pos] = i;
+            pout[(int64_t)row * N + pos] = o;
+            if (is_subm) {   // mirrored entry, indices.py:1696-1699
+                pin[(int64_t)(kv - 1 - row) * N + pos] = o;
+                pout[(int64_t)(kv - 1 - row) * N + pos] = i;
+            }
+            ++pos;
+        }
+    }
+}
+
+__global__ void subm_centre_kernel(int32_t *__restrict__ pairs, int64_t N, int kv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    pairs[(int64_t)(kv / 2) * N + i] = (int32_t)i;
+    pairs[(int64_t)kv * N + (int64_t)(kv / 2) * N + i] = (int32_t)i;
+}
+
+// compact pairs -> dense tables (ConvAlgo.Native operator path)
+__global__ void pairs_to_table_kernel(const int32_t *__restrict__ pairs, const int32_t *__restrict__ num, int kv,
+                                      int64_t pair_stride, int64_t n_in, int64_t n_out, int is_subm, int inverse,
+                                      int32_t *__restrict__ table_fwd, int32_t *__restrict__ table_bwd,
+                                      uint32_t *__restrict__ mask_fwd, uint32_t *__restrict__ mask_bwd, int words) {
+    int k = blockIdx.y;
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t cnt;
+    if (is_subm) {   // mirror rule, spconv/pytorch/ops.py:962-968
+        if (k == kv / 2) cnt = n_in;
+        else cnt = k < kv / 2 ? num[k] : num[kv - 1 - k];
+    } else {
+        cnt = num[k];
+    }
+    if (j >= cnt) return;
+    int32_t a = pairs[(int64_t)k * pair_stride + j];
+    int32_t b = pairs[(int64_t)kv * pair_stride + (int64_t)k * pair_stride + j];
+    int32_t i = inverse ? b : a, o = inverse ? a : b;
+    if (i < 0 || o < 0 || i >= n_in || o >= n_out) return;
+    if (table_fwd) table_fwd[(int64_t)k * n_out + o] = i;
+    if (table_bwd) table_bwd[(int64_t)k * n_in + i] = o;
+    if (mask_fwd) atomicOr(&mask_fwd[o * words + (k >> 5)], 1u << (k & 31));
+    if (mask_bwd) atomicOr(&mask_bwd[i * words + (k >> 5)], 1u << (k & 31));
+}
+
+// ------------------------------------------------------------------ argsort helpers
+__global__ void iota_kernel(int32_t *__restrict__ p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+__global__ void gather_word_kernel(const uint32_t *__restrict__ mask, const int32_t *__restrict__ perm, int64_t n,
+                                   int words, int w, uint32_t *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = mask[(int64_t)perm[i] * words + w];
+}
+__global__ void gather_rows_kernel(const uint32_t *__restrict__ src, const int32_t *__restrict__ perm, int64_t n,
+                                   int words, uint32_t *__restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < words; ++w) dst[i * words + w] = src[(int64_t)perm[i] * words + w];
+}
+
+}  // namespace spx
+
+using namespace spx;
+
+// ====================================================================== C ABI
+static int validate_geom(const spx_conv_geometry *g) {
+    SPX_REQUIRE(g != nullptr, "geometry is NULL");
+    SPX_REQUIRE(g->ndim >= 1 && g->ndim <= SPX_MAX_NDIM, "ndim must be in [1, %d], got %d", SPX_MAX_NDIM, g->ndim);
+    SPX_REQUIRE(g->batch_size > 0, "batch_size must be positive");
+    for (int a = 0; a < g->ndim; ++a) {
+        SPX_REQUIRE(g->ksize[a] > 0 && g->dilation[a] > 0 && g->in_dims[a] > 0, "bad ksize/dilation/dims on axis %d", a);
+    }
+    return 0;
+}
+
+struct RbLayout {   // workspace layout shared by the rulebook entry points
+    size_t table_bytes, table_vals_bytes;
+    uint32_t capacity;
+    bool i64;
+};
+
+static RbLayout rb_layout(const Geom &g, int64_t items, const int *dims) {
+    RbLayout L;
+    L.i64 = needs_i64(g, dims);
+    L.capacity = table_capacity(items);
+    L.table_bytes = (size_t)L.capacity * 8;
+    L.table_vals_bytes = L.i64 ? (size_t)L.capacity * 4 : 0;
+    return L;
+}
+
+extern "C" int64_t spx_conv_max_out(const spx_conv_geometry *g, int64_t num_in) {
+    // all.py:1559-1580, with the transposed case bounded by kv*N (ops.py:569-570)
+    int64_t res = num_in, kv = 1;
+    for (int i = 0; i < g->ndim; ++i) {
+        kv *= g->ksize[i];
+        if (g->ksize[i] > g->stride[i]) res *= (g->ksize[i] + g->stride[i] - 1) / g->stride[i];
+    }
+    if (g->transposed) res = kv * num_in;
+    if (res > kv * num_in) res = kv * num_in;
+    return res;
+}
+
+static size_t sort_pairs_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    return bytes;
+}
+
+extern "C" size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_t num_in, int64_t max_out, int is_subm) {
+    if (!g || g->ndim < 1 || g->ndim > SPX_MAX_NDIM) return 0;
+    Geom gg = make_geom(g, is_subm != 0);
+    size_t total = 256;
+    if (is_subm) {
+        RbLayout L = rb_layout(gg, num_in, gg.in_dims);
+        total += align_up(L.table_bytes, 256) + align_up(L.table_vals_bytes, 256);
+    } else {
+        max_out = spx_conv_max_out(g, num_in);   // the bound is recomputed by both stages
+        RbLayout L = rb_layout(gg, max_out, gg.out_dims);
+        total += align_up(L.table_bytes, 256) + align_up(L.table_vals_bytes, 256);
+        total += 4 * align_up((size_t)max_out * 4, 256);          // payload, slot (in + out)
+        total += align_up(sort_pairs_temp_bytes(max_out), 256);
+        total += 256;                                             // counter
+    }
+    return total + 1024;
+}
+
+extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indices, int64_t N, int32_t *pair_fwd,
+                                 int32_t *pair_bwd, uint32_t *mask, void *workspace, size_t workspace_bytes,
+                                 spx_stream_t stream_) {
+    if (validate_geom(g)) return 2;
+    for (int a = 0; a < g->ndim; ++a)
+        SPX_REQUIRE(g->ksize[a] % 2 == 1, "subm only support odd ksize");
+    SPX_REQUIRE(N >= 0 && N < 2147483647ll, "bad N");
+    if (N == 0) return 0;
+    SPX_REQUIRE(indices && pair_fwd && workspace, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Geom gg = make_geom(g, true);
+    SPX_REQUIRE((int64_t)gg.kv * N < 2147483647ll * 4, "kv*N too large");
+    RbLayout L = rb_layout(gg, N, gg.in_dims);
+    WorkspaceCarver ws(workspace, workspace_bytes);
+    void *tbl = ws.take<char>(L.table_bytes);
+    int32_t *tvals = L.i64 ? ws.take<int32_t>(L.capacity) : nullptr;
+    SPX_REQUIRE(ws.ok(), "rulebook workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+    int words = (gg.kv + 31) / 32;
+    const int T = 128;
+    unsigned nblk = (unsigned)div_up64(N, T);
+    SPX_CHECK_CUDA(cudaMemsetAsync(tbl, 0xFF, L.table_bytes, stream));
+    if (!L.i64) {
+        Table32 t{(unsigned long long *)tbl, L.capacity - 1};
+        subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
+        SPX_CHECK_LAUNCH("subm_insert_kernel");
+        subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
+        SPX_CHECK_LAUNCH("subm_probe_kernel");
+    } else {
+        SPX_CHECK_CUDA(cudaMemsetAsync(tvals, 0x7F, (size_t)L.capacity * 4, stream));
+        Table64 t{(long long *)tbl, tvals, L.capacity - 1};
+        subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
+        SPX_CHECK_LAUNCH("subm_insert_kernel");
+        subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
+        SPX_CHECK_LAUNCH("subm_probe_kernel");
+    }
+    return 0;
+}
+
+namespace {
+struct ConvWs {
+    void *tbl; int32_t *tvals;
+    uint32_t *payload, *slot, *payload_sorted, *slot_sorted;
+    void *sort_tmp; size_t sort_tmp_bytes;
+    int *counter;
+    RbLayout L;
+};
+int carve_conv_ws(const spx_conv_geometry *g, const Geom &gg, int64_t N, void *workspace, size_t bytes, ConvWs &w) {
+    int64_t max_out = spx_conv_max_out(g, N);
+    w.L = rb_layout(gg, max_out, gg.out_dims);
+    WorkspaceCarver ws(workspace, bytes);
+    w.tbl = ws.take<char>(w.L.table_bytes);
+    w.tvals = w.L.i64 ? ws.take<int32_t>(w.L.capacity) : nullptr;
+    w.payload = ws.take<uint32_t>(max_out);
+    w.slot = ws.take<uint32_t>(max_out);
+    w.payload_sorted = ws.take<uint32_t>(max_out);
+    w.slot_sorted = ws.take<uint32_t>(max_out);
+    w.sort_tmp_bytes = sort_pairs_temp_bytes(max_out);
+    w.sort_tmp = ws.take<char>(w.sort_tmp_bytes);
+    w.counter = ws.take<int>(64);
+    SPX_REQUIRE(ws.ok(), "rulebook workspace too small: need %zu, have %zu", ws.off, bytes);
+    return 0;
+}
+}  // namespace
+
+extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                                        int64_t *num_out_host, void *workspace, size_t workspace_bytes,
+                                        spx_stream_t stream_) {
+    if (validate_geom(g)) return 2;
+    SPX_REQUIRE(num_out_host != nullptr, "num_out_host is NULL");
+    *num_out_host = 0;
+    if (N == 0) return 0;
+    SPX_REQUIRE(indices && workspace, "NULL pointer argument");
+    for (int a = 0; a < g->ndim; ++a)
+        SPX_REQUIRE(g->stride[a] > 0 && g->out_dims[a] > 0, "bad stride/out_dims on axis %d", a);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Geom gg = make_geom(g, false);
+    SPX_REQUIRE((int64_t)gg.kv * N < 2000000000ll, "kv*N must stay below 2e9 (kv=%d, N=%lld)", gg.kv, (long long)N);
+    ConvWs w;
+    if (carve_conv_ws(g, gg, N, workspace, workspace_bytes, w)) return 2;
+    const int T = 128;
+    dim3 grid((unsigned)div_up64(N, T), gg.kv);
+    SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
+    SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
+    unsigned cblk = (w.L.capacity + 255) / 256;
+    if (!w.L.i64) {
+        Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
+        conv_insert_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N);
+        SPX_CHECK_LAUNCH("conv_insert_kernel");
+        conv_collect_kernel<<<cblk, 256, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
+        SPX_CHECK_LAUNCH("conv_collect_kernel");
+    } else {
+        SPX_CHECK_CUDA(cudaMemsetAsync(w.tvals, 0x7F, (size_t)w.L.capacity * 4, stream));
+        Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
+        conv_insert_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N);
+        SPX_CHECK_LAUNCH("conv_insert_kernel");
+        conv_collect_kernel<<<cblk, 256, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
+        SPX_CHECK_LAUNCH("conv_collect_kernel");
+    }
+    int m_host = 0;
+    SPX_CHECK_CUDA(cudaMemcpyAsync(&m_host, w.counter, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SPX_CHECK_CUDA(cudaStreamSynchronize(stream));
+    *num_out_host = m_host;
+    if (m_host == 0) return 0;
+    // rank outputs by first touch: sort (payload, slot) by payload; payload < kv*N
+    int end_bit = 1;
+    while (end_bit < 32 && ((int64_t)1 << end_bit) < (int64_t)gg.kv * N) ++end_bit;
+    size_t tmp_bytes = w.sort_tmp_bytes;
+    SPX_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp_bytes, w.payload, w.payload_sorted, w.slot,
+                                                   w.slot_sorted, m_host, 0, end_bit, stream));
+    count_launch(3);
+    return 0;
+}
+
+extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_t *indices, int64_t N, int64_t M,
+                                        int32_t *out_inds, int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask_fwd,
+                                        uint32_t *mask_bwd, void *workspace, size_t workspace_bytes,
+                                        spx_stream_t stream_) {
+    if (validate_geom(g)) return 2;
+    if (N == 0 || M == 0) return 0;
+    SPX_REQUIRE(indices && out_inds && pair_fwd && pair_bwd && workspace, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Geom gg = make_geom(g, false);
+    ConvWs w;
+    if (carve_conv_ws(g, gg, N, workspace, workspace_bytes, w)) return 2;
+    int words = (gg.kv + 31) / 32;
+    const int T = 128;
+    dim3 grid((unsigned)div_up64(N, T), gg.kv);
+    SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));
+    if (!w.L.i64) {
+        Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
+        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
+        SPX_CHECK_LAUNCH("conv_assign_kernel");
+        conv_pairs_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        SPX_CHECK_LAUNCH("conv_pairs_kernel");
+    } else {
+        Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
+        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
+        SPX_CHECK_LAUNCH("conv_assign_kernel");
+        conv_pairs_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        SPX_CHECK_LAUNCH("conv_pairs_kernel");
+    }
+    if (mask_fwd) {
+        table_mask_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(pair_fwd, M, gg.kv, words, mask_fwd);
+        SPX_CHECK_LAUNCH("table_mask_kernel");
+    }
+    if (mask_bwd) {
+        table_mask_kernel<<<(unsigned)div_up64(N, 256), 256, 0, stream>>>(pair_bwd, N, gg.kv, words, mask_bwd);
+        SPX_CHECK_LAUNCH("table_mask_kernel");
+    }
+    return 0;
+}
+
+extern "C" size_t spx_native_pairs_workspace_size(int64_t N, int kv) {
+    int64_t nblk = div_up64(N > 0 ? N : 1, SCAN_TILE);
+    return (size_t)kv * nblk * sizeof(int) + 1024;
+}
+
+extern "C" int spx_native_pairs(const int32_t *pair_bwd, int64_t N, int kv, int is_subm, int32_t *pairs,
+                                int32_t *indice_pair_num, void *workspace, size_t workspace_bytes,
+                                spx_stream_t stream_) {
+    SPX_REQUIRE(kv > 0 && N >= 0, "bad kv / N");
+    SPX_REQUIRE(pairs && indice_pair_num, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SPX_CHECK_CUDA(cudaMemsetAsync(indice_pair_num, 0, sizeof(int32_t) * kv, stream));
+    if (N == 0) return 0;
+    SPX_REQUIRE(pair_bwd && workspace, "NULL pointer argument");
+    SPX_CHECK_CUDA(cudaMemsetAsync(pairs, 0xFF, (size_t)2 * kv * N * 4, stream));
+    int rows = is_subm ? kv / 2 : kv;
+    int nblk = (int)div_up64(N, SCAN_TILE);
+    WorkspaceCarver ws(workspace, workspace_bytes);
+    int *counts = ws.take<int>((size_t)kv * nblk);
+    SPX_REQUIRE(ws.ok(), "native-pairs workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+    if (rows > 0) {
+        dim3 grid(nblk, rows);
+        native_count_kernel<<<grid, SCAN_THREADS, 0, stream>>>(pair_bwd, N, counts, nblk);
+        SPX_CHECK_LAUNCH("native_count_kernel");
+        native_scan_kernel<<<rows, SCAN_THREADS, 0, stream>>>(counts, nblk, indice_pair_num);
+        SPX_CHECK_LAUNCH("native_scan_kernel");
+        native_write_kernel<<<grid, SCAN_THREADS, 0, stream>>>(pair_bwd, N, kv, is_subm, counts, nblk, pairs);
+        SPX_CHECK_LAUNCH("native_write_kernel");
+    }
+    if (is_subm) {
+        subm_centre_kernel<<<(unsigned)div_up64(N, 256), 256, 0, stream>>>(pairs, N, kv);
+        SPX_CHECK_LAUNCH("subm_centre_kernel");
+    }
+    return 0;
+}
+
+extern "C" int spx_pairs_to_table(const int32_t *pairs, const int32_t *indice_pair_num, int kv, int64_t pair_stride,
+                                  int64_t n_in, int64_t n_out, int is_subm, int inverse, int32_t *table_fwd,
+                                  int32_t *table_bwd, uint32_t *mask_fwd, uint32_t *mask_bwd, spx_stream_t stream_) {
+    SPX_REQUIRE(pairs && indice_pair_num && kv > 0, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int words = (kv + 31) / 32;
+    if (table_fwd && n_out > 0) SPX_CHECK_CUDA(cudaMemsetAsync(table_fwd, 0xFF, (size_t)kv * n_out * 4, stream));
+    if (table_bwd && n_in > 0) SPX_CHECK_CUDA(cudaMemsetAsync(table_bwd, 0xFF, (size_t)kv * n_in * 4, stream));
+    if (mask_fwd && n_out > 0) SPX_CHECK_CUDA(cudaMemsetAsync(mask_fwd, 0, (size_t)n_out * words * 4, stream));
+    if (mask_bwd && n_in > 0) SPX_CHECK_CUDA(cudaMemsetAsync(mask_bwd, 0, (size_t)n_in * words * 4, stream));
+    int64_t span = pair_stride;
+    if (span <= 0) return 0;
+    dim3 grid((unsigned)div_up64(span, 256), kv);
+    pairs_to_table_kernel<<<grid, 256, 0, stream>>>(pairs, indice_pair_num, kv, pair_stride, n_in, n_out, is_subm,
+                                                    inverse, table_fwd, table_bwd, mask_fwd, mask_bwd, words);
+    SPX_CHECK_LAUNCH("pairs_to_table_kernel");
+    return 0;
+}
+
+extern "C" size_t spx_mask_argsort_workspace_size(int64_t N, int words) {
+    if (N <= 0) return 256;
+    size_t n = (size_t)N;
+    return 4 * align_up(n * 4, 256) + align_up(n * 4 * (size_t)words, 256) + align_up(sort_pairs_temp_bytes(N), 256) + 1024;
+}
+
+extern "C" int spx_mask_argsort(uint32_t *mask, int32_t *argsort, int64_t N, int words, int kv, int do_sort,
+                                void *workspace, size_t workspace_bytes, spx_stream_t stream_) {
+    SPX_REQUIRE(words >= 1 && words <= 4, "mask words must be in [1,4], got %d", words);
+    if (N == 0) return 0;
+    SPX_REQUIRE(mask && argsort, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned nblk = (unsigned)div_up64(N, 256);
+    if (!do_sort) {
+        iota_kernel<<<nblk, 256, 0, stream>>>(argsort, N);
+        SPX_CHECK_LAUNCH("iota_kernel");
+        return 0;
+    }
+    SPX_REQUIRE(workspace != nullptr, "workspace is NULL");
+    WorkspaceCarver ws(workspace, workspace_bytes);
+    uint32_t *keys_in = ws.take<uint32_t>(N);
+    uint32_t *keys_out = ws.take<uint32_t>(N);
+    int32_t *perm_a = ws.take<int32_t>(N);
+    int32_t *perm_b = ws.take<int32_t>(N);
+    uint32_t *rows_tmp = ws.take<uint32_t>((size_t)N * words);
+    size_t tmp_bytes = sort_pairs_temp_bytes(N);
+    void *tmp = ws.take<char>(tmp_bytes);
+    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+    iota_kernel<<<nblk, 256, 0, stream>>>(perm_a, N);
+    SPX_CHECK_LAUNCH("iota_kernel");
+    if (words == 1) {
+        int end_bit = kv > 0 && kv < 32 ? kv : 32;
+        SPX_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint32_t *)mask, keys_out,
+                                                       (const int32_t *)perm_a, argsort, (int)N, 0, end_bit, stream));
+        count_launch(3);
+        SPX_CHECK_CUDA(cudaMemcpyAsync(mask, keys_out, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+        return 0;
+    }
+    // LSD over words: least significant word (last) first; stable sorts compose
+    int32_t *cur = perm_a, *nxt = perm_b;
+    for (int w = words - 1; w >= 0; --w) {
+        gather_word_kernel<<<nblk, 256, 0, stream>>>(mask, cur, N, words, w, keys_in);
+        SPX_CHECK_LAUNCH("gather_word_kernel");
+        SPX_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint32_t *)keys_in, keys_out,
+                                                       (const int32_t *)cur, nxt, (int)N, 0, 32, stream));
+        count_launch(3);
+        int32_t *t = cur; cur = nxt; nxt = t;
+    }
+    SPX_CHECK_CUDA(cudaMemcpyAsync(argsort, cur, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+    gather_rows_kernel<<<nblk, 256, 0, stream>>>(mask, argsort, N, words, rows_tmp);
+    SPX_CHECK_LAUNCH("gather_rows_kernel");
+    SPX_CHECK_CUDA(cudaMemcpyAsync(mask, rows_tmp, (size_t)N * words * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}

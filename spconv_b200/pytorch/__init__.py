@@ -1,0 +1,12 @@
+"""``import spconv_b200.pytorch as spconv`` -- the ``spconv.pytorch`` surface of the hot path."""
+from ..core import Activation, AlgoHint, ConvAlgo  # noqa: F401
+from . import functional, ops  # noqa: F401
+from .conv import (SparseConv1d, SparseConv2d, SparseConv3d, SparseConv4d,  # noqa: F401
+                   SparseConvolution, SparseConvTranspose1d, SparseConvTranspose2d,
+                   SparseConvTranspose3d, SparseConvTranspose4d, SparseInverseConv1d,
+                   SparseInverseConv2d, SparseInverseConv3d, SparseInverseConv4d, SubMConv1d,
+                   SubMConv2d, SubMConv3d, SubMConv4d)
+from .core import (CUDAKernelTimer, ImplicitGemmIndiceData, IndiceData,  # noqa: F401
+                   SparseConvTensor, scatter_nd)
+from .modules import (RemoveGrid, SparseBatchNorm, SparseIdentity, SparseModule,  # noqa: F401
+                      SparseReLU, SparseSequential, ToDense, assign_name_for_sparse_modules)

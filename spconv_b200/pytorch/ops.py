@@ -1,0 +1,511 @@
+"""Operator layer: the drop-in boundary of the hot path.
+
+Same function names, argument order and return shapes as ``spconv/pytorch/ops.py``
+(``get_indice_pairs`` :132, ``get_indice_pairs_implicit_gemm`` :329, ``indice_conv`` :811,
+``indice_conv_backward`` :1103, ``implicit_gemm`` :1450, ``implicit_gemm_backward`` :1667),
+implemented as thin calls into the C-ABI library (``include/spconv_b200.h``) on the current
+CUDA stream.  CUDA tensors only: there is deliberately no CPU path in the product.
+
+Differences a reference user can observe (all documented in DESIGN.md):
+  * rulebooks are deterministic and bit-equal to the reference's CPU order;
+  * ``mask_width`` is always 128 (the tcgen05 tile height);
+  * ``ConvAlgo.MaskSplitImplicitGemm`` is executed as ``MaskImplicitGemm`` (one mask split).
+"""
+from __future__ import annotations
+
+import ctypes
+import functools
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..constants import SPCONV_ALLOW_TF32, SPCONV_DO_SORT
+from ..core import Activation, ConvAlgo
+from .core import CUDAKernelTimer, ThrustSortAllocator
+
+INT32_MAX = 2147483647
+MASK_WIDTH = 128
+
+_DTYPE_CODE = {
+    torch.float32: _cabi.SPX_F32,
+    torch.float16: _cabi.SPX_F16,
+    torch.bfloat16: _cabi.SPX_BF16,
+    torch.int8: _cabi.SPX_I8,
+}
+
+
+# ---------------------------------------------------------------------------- small helpers
+def _lib():
+    return _cabi.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"spconv_b200: {what} must be a CUDA tensor. This engine has no CPU path "
+            "(the CPU restatement under oracle/ is test infrastructure only).")
+
+
+def _bytes(n: int, device, alloc: Optional[ThrustSortAllocator] = None) -> torch.Tensor:
+    if alloc is not None:
+        return alloc.get(n)
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def _act_code(act_type) -> int:
+    if act_type is None:
+        return _cabi.SPX_ACT_NONE
+    if isinstance(act_type, Activation):
+        return act_type.value
+    return int(getattr(act_type, "value", act_type))
+
+
+def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
+    """``(in + 2p - d(k-1) - 1) // s + 1`` per axis; ``k == -1`` means global (size 1)."""
+    return [1 if k == -1 else (i + 2 * p - d * (k - 1) - 1) // s + 1
+            for i, k, s, p, d in zip(input_size, kernel_size, stride, padding, dilation)]
+
+
+def get_deconv_output_size(input_size, kernel_size, stride, padding, dilation, output_padding):
+    out = []
+    for i, k, s, p, op in zip(input_size, kernel_size, stride, padding, output_padding):
+        if k == -1:
+            raise ValueError("deconv don't support kernel_size < 0")
+        out.append((i - 1) * s - 2 * p + k + op)
+    return out
+
+
+_VANISHED = ("Your points vanished here, this usually because you provide conv params that "
+             "may ignore some input points. Example: spatial_shape=[8, 200, 200] -> "
+             "[3, 3, 3] kernel, [2, 2, 2] stride, no padding -> out shape [3, 99, 99]; "
+             "points in z=7/8 are dropped when no point lies in z<=6.")
+
+
+def _out_shape(spatial_shape, ksize, stride, padding, dilation, out_padding, subm, transpose):
+    if subm:
+        shape = list(spatial_shape)
+    elif transpose:
+        shape = get_deconv_output_size(spatial_shape, ksize, stride, padding, dilation, out_padding)
+    else:
+        shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+    if any(x <= 0 for x in shape):
+        raise ValueError(
+            f"your out spatial shape {shape} reach zero!!! input shape: {spatial_shape}")
+    return shape
+
+
+def _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding, dilation,
+              transpose):
+    ndim = indices.shape[1] - 1
+    if not (1 <= ndim <= _cabi.SPX_MAX_NDIM):
+        raise RuntimeError(f"unsupported ndim {ndim}")
+    return _cabi.make_geometry(ndim, batch_size, spatial_shape, out_shape, ksize, stride, padding,
+                               dilation, transpose)
+
+
+def _conv_rulebook(geo, indices, n_in, kv, words, want_masks, alloc):
+    """Two-phase regular-conv rulebook; returns (out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd)."""
+    lib = _lib()
+    dev = indices.device
+    ws_bytes = lib.spx_rulebook_workspace_size(ctypes.byref(geo), n_in, 0, 0)
+    ws = _bytes(ws_bytes, dev, alloc)
+    m_host = ctypes.c_int64(0)
+    _cabi.check(lib.spx_conv_rulebook_stage1(ctypes.byref(geo), _ptr(indices), n_in,
+                                             ctypes.byref(m_host), ws.data_ptr(), ws.numel(),
+                                             _stream()), "conv_rulebook_stage1")
+    m = int(m_host.value)
+    if m == 0:
+        raise ValueError(_VANISHED)
+    ndim = indices.shape[1] - 1
+    out_inds = torch.empty((m, ndim + 1), dtype=torch.int32, device=dev)
+    pair_fwd = torch.empty((kv, m), dtype=torch.int32, device=dev)
+    pair_bwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+    mask_fwd = torch.empty((1, m, words), dtype=torch.int32, device=dev) if want_masks else None
+    mask_bwd = torch.empty((1, n_in, words), dtype=torch.int32, device=dev) if want_masks else None
+    _cabi.check(lib.spx_conv_rulebook_stage2(ctypes.byref(geo), _ptr(indices), n_in, m,
+                                             out_inds.data_ptr(), pair_fwd.data_ptr(),
+                                             pair_bwd.data_ptr(), _ptr(mask_fwd), _ptr(mask_bwd),
+                                             ws.data_ptr(), ws.numel(), _stream()),
+                "conv_rulebook_stage2")
+    return out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd
+
+
+def _argsort_masks(mask: torch.Tensor, kv: int, do_sort: bool, alloc) -> torch.Tensor:
+    """mask [1, n, words] -> argsort [1, n]; mask is left sorted (thrust::sort_by_key semantics,
+    ``spconv/csrc/sparse/all.py:935-1000``)."""
+    lib = _lib()
+    n, words = mask.shape[1], mask.shape[2]
+    argsort = torch.empty((1, n), dtype=torch.int32, device=mask.device)
+    if n == 0:
+        return argsort
+    ws_bytes = lib.spx_mask_argsort_workspace_size(n, words)
+    ws = _bytes(ws_bytes, mask.device, alloc)
+    _cabi.check(lib.spx_mask_argsort(mask.data_ptr(), argsort.data_ptr(), n, words, kv,
+                                     int(bool(do_sort)), ws.data_ptr(), ws.numel(), _stream()),
+                "mask_argsort")
+    return argsort
+
+
+# ---------------------------------------------------------------------------- rulebooks
+def get_indice_pairs(indices: torch.Tensor, batch_size: int, spatial_shape: List[int],
+                     algo: ConvAlgo, ksize: List[int], stride: List[int], padding: List[int],
+                     dilation: List[int], out_padding: List[int], subm: bool = False,
+                     transpose: bool = False, num_out_act_bound: int = -1):
+    """ConvAlgo.Native rulebook: ``(out_inds [M, ndim+1], pairs [2, kv, N], indice_pair_num [kv])``
+    with pair ORDER equal to the reference CPU implementation
+    (``spconv/csrc/sparse/indices.py:1640-1778``)."""
+    _require_cuda(indices, "indices")
+    lib = _lib()
+    dev = indices.device
+    indices = indices.contiguous()
+    n_in = indices.shape[0]
+    kv = int(np.prod(ksize))
+    out_shape = _out_shape(spatial_shape, ksize, stride, padding, dilation, out_padding, subm,
+                           transpose)
+    geo = _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding,
+                    dilation, transpose)
+    pairs = torch.empty((2, kv, n_in), dtype=torch.int32, device=dev)
+    num = torch.empty((kv,), dtype=torch.int32, device=dev)
+    if subm:
+        for k in ksize:
+            if k % 2 != 1:
+                raise RuntimeError("subm only support odd ksize")
+        pair_fwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+        pair_bwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+        ws = _bytes(lib.spx_rulebook_workspace_size(ctypes.byref(geo), n_in, 0, 1), dev)
+        _cabi.check(lib.spx_subm_rulebook(ctypes.byref(geo), _ptr(indices), n_in,
+                                          pair_fwd.data_ptr(), pair_bwd.data_ptr(), None,
+                                          ws.data_ptr(), ws.numel(), _stream()), "subm_rulebook")
+        out_inds = indices
+    else:
+        out_inds, pair_fwd, pair_bwd, _, _ = _conv_rulebook(geo, indices, n_in, kv,
+                                                            (kv + 31) // 32, False, None)
+    ws2 = _bytes(lib.spx_native_pairs_workspace_size(n_in, kv), dev)
+    _cabi.check(lib.spx_native_pairs(_ptr(pair_bwd), n_in, kv, int(subm), pairs.data_ptr(),
+                                     num.data_ptr(), ws2.data_ptr(), ws2.numel(), _stream()),
+                "native_pairs")
+    return out_inds, pairs, num
+
+
+def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
+                                   spatial_shape: List[int], algo: ConvAlgo, ksize: List[int],
+                                   stride: List[int], padding: List[int], dilation: List[int],
+                                   out_padding: List[int], subm: bool = False,
+                                   transpose: bool = False, is_train: bool = True,
+                                   alloc: Optional[ThrustSortAllocator] = None,
+                                   timer: CUDAKernelTimer = CUDAKernelTimer(False),
+                                   num_out_act_bound: int = -1,
+                                   direct_table: bool = True,
+                                   do_sort=SPCONV_DO_SORT):
+    """Masked implicit-GEMM rulebook.  Returns the reference's 9-tuple
+    ``(out_inds, indice_num_per_loc, pair_fwd, pair_bwd, [mask_fwd], [mask_bwd],
+    [argsort_fwd], [argsort_bwd], masks)`` (``ops.py:329-359``)."""
+    _require_cuda(indices, "indices")
+    assert algo in (ConvAlgo.MaskImplicitGemm, ConvAlgo.MaskSplitImplicitGemm), "TODO"
+    lib = _lib()
+    dev = indices.device
+    indices = indices.contiguous()
+    n_in = indices.shape[0]
+    kv = int(np.prod(ksize))
+    words = (kv + 31) // 32
+    if kv > 128:
+        raise NotImplementedError("masked implicit gemm supports kernel volume <= 128")
+    out_shape = _out_shape(spatial_shape, ksize, stride, padding, dilation, out_padding, subm,
+                           transpose)
+    geo = _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding,
+                    dilation, transpose)
+    masks = [np.array([0xffffffff], dtype=np.uint32)]
+    # per-offset pair counts are not consumed by the GEMM; kept for API shape
+    indice_num_per_loc = torch.zeros((kv,), dtype=torch.int32, device=dev)
+    if subm:
+        for k in ksize:
+            if k % 2 != 1:
+                raise RuntimeError("subm only support odd ksize")
+        pair = torch.empty((2 if is_train else 1, kv, n_in), dtype=torch.int32, device=dev)
+        pair_mask = torch.empty((1, n_in, words), dtype=torch.int32, device=dev)
+        with timer.record("gen_subm_inds", _stream()):
+            ws = _bytes(lib.spx_rulebook_workspace_size(ctypes.byref(geo), n_in, 0, 1), dev, alloc)
+            _cabi.check(lib.spx_subm_rulebook(ctypes.byref(geo), _ptr(indices), n_in,
+                                              pair[0].data_ptr(),
+                                              pair[1].data_ptr() if is_train and n_in else None,
+                                              _ptr(pair_mask), ws.data_ptr(), ws.numel(),
+                                              _stream()), "subm_rulebook")
+        with timer.record("gen_subm_inds_sort", _stream()):
+            mask_argsort = _argsort_masks(pair_mask, kv, do_sort, alloc)
+        pair_bwd = pair[1] if is_train else torch.Tensor()
+        return (indices, indice_num_per_loc, pair[0], pair_bwd, [pair_mask[0]], [],
+                [mask_argsort[0]], [], masks)
+    with timer.record("gen_conv_inds", _stream()):
+        out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd = _conv_rulebook(
+            geo, indices, n_in, kv, words, True, alloc)
+    with timer.record("gen_conv_inds_sort", _stream()):
+        argsort_fwd = _argsort_masks(mask_fwd, kv, do_sort, alloc)
+        if is_train:
+            argsort_bwd = _argsort_masks(mask_bwd, kv, do_sort, alloc)
+    if is_train:
+        return (out_inds, indice_num_per_loc, pair_fwd, pair_bwd, [mask_fwd[0]], [mask_bwd[0]],
+                [argsort_fwd[0]], [argsort_bwd[0]], masks)
+    return (out_inds, indice_num_per_loc, pair_fwd, pair_bwd, [mask_fwd[0]], [], [argsort_fwd[0]],
+            [], masks)
+
+
+# ---------------------------------------------------------------------------- GEMM descriptor
+def _f32_mode() -> int:
+    return _cabi.SPX_F32_TF32 if SPCONV_ALLOW_TF32 else _cabi.SPX_F32_EXACT
+
+
+def _desc(dtype, kv, c_in, c_out, n_in, n_out, pair, mask, argsort, reverse=False):
+    d = _cabi.GemmDesc()
+    d.dtype = _DTYPE_CODE[dtype]
+    d.f32_mode = _f32_mode()
+    d.kv, d.c_in, d.c_out = int(kv), int(c_in), int(c_out)
+    d.n_in, d.n_out = int(n_in), int(n_out)
+    d.pair = _ptr(pair)
+    d.pair_stride = int(pair.stride(0)) if pair is not None and pair.dim() == 2 else 0
+    d.mask = _ptr(mask)
+    d.argsort = _ptr(argsort)
+    d.reverse_offsets = int(bool(reverse))
+    return d
+
+
+def _check_filter(features, filters):
+    if filters.dtype != features.dtype:
+        raise RuntimeError(f"features ({features.dtype}) and filters ({filters.dtype}) must have the same dtype")
+    if features.dtype not in _DTYPE_CODE:
+        raise RuntimeError(f"unsupported dtype {features.dtype}")
+    kv = int(np.prod(filters.shape[1:-1]))
+    return kv, int(filters.shape[-1]), int(filters.shape[0])
+
+
+def _first(split_list):
+    if isinstance(split_list, (list, tuple)):
+        return split_list[0] if len(split_list) else None
+    return split_list
+
+
+# ---------------------------------------------------------------------------- masked implicit GEMM
+def implicit_gemm(features: torch.Tensor, filters: torch.Tensor, pair_fwd: torch.Tensor,
+                  pair_mask_fwd_splits: List[torch.Tensor],
+                  mask_argsort_fwd_splits: List[torch.Tensor], num_activate_out: int,
+                  masks: List[np.ndarray], is_train: bool, is_subm: bool,
+                  timer: CUDAKernelTimer = CUDAKernelTimer(False),
+                  fp32_accum: Optional[bool] = None, bias: Optional[torch.Tensor] = None,
+                  act_alpha: float = 0.0, act_beta: float = 0.0,
+                  act_type=Activation.None_, output_scale: float = 1.0,
+                  scale: Optional[torch.Tensor] = None, output_add: Optional[torch.Tensor] = None,
+                  output_add_scale: float = 0.0, output_dtype: Optional[torch.dtype] = None):
+    """Forward masked implicit GEMM -> ``(out [M, K], mask_output_fwd, mask_width)``
+    (``ops.py:1450-1469`` / ``convops.py:2075-2243``).  Accumulation is always fp32 in TMEM
+    (``fp32_accum`` is accepted and ignored)."""
+    _require_cuda(features, "features")
+    lib = _lib()
+    features = features.contiguous()
+    filters = filters.contiguous()
+    kv, c_in, c_out = _check_filter(features, filters)
+    assert features.shape[1] == c_in, "channel size mismatch"
+    n_in, n_out = features.shape[0], int(num_activate_out)
+    mask = _first(pair_mask_fwd_splits)
+    argsort = _first(mask_argsort_fwd_splits)
+    is_int8 = features.dtype == torch.int8
+    if output_dtype is None:
+        output_dtype = features.dtype
+    words = (kv + 31) // 32
+    mask_output = torch.empty((1, (n_out + MASK_WIDTH - 1) // MASK_WIDTH, words), dtype=torch.int32,
+                              device=features.device) if is_train else torch.Tensor()
+    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask, argsort)
+    if is_int8:
+        assert scale is not None, "int8 implicit gemm needs the per-channel scale"
+        out = torch.empty((n_out, c_out), dtype=output_dtype, device=features.device)
+        scale_f = (scale.float() * float(output_scale)).contiguous() if output_scale != 1.0 else scale.float().contiguous()
+        bias_f = bias.float().contiguous() if bias is not None else None
+        with timer.record("implicit_gemm_int8", _stream()):
+            _cabi.check(lib.spx_implicit_gemm_fwd_int8(
+                ctypes.byref(d), _ptr(features), _ptr(filters), _ptr(out), _DTYPE_CODE[output_dtype],
+                _ptr(scale_f), _ptr(bias_f), _ptr(output_add), float(output_add_scale),
+                _act_code(act_type), float(act_alpha), _stream()), "implicit_gemm_fwd_int8")
+        return out, mask_output, MASK_WIDTH
+    out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
+    if bias is not None:
+        bias = bias.to(features.dtype).contiguous()
+    with timer.record("implicit_gemm", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_fwd(ctypes.byref(d), _ptr(features), _ptr(filters),
+                                              _ptr(out), _ptr(bias), _act_code(act_type),
+                                              float(act_alpha), _ptr(mask_output) if is_train else None,
+                                              _stream()), "implicit_gemm_fwd")
+    if output_add is not None:
+        out = out + output_add
+    if output_dtype != out.dtype:
+        out = out.to(output_dtype)
+    return out, mask_output, MASK_WIDTH
+
+
+def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: torch.Tensor,
+                           pair_fwd: torch.Tensor, pair_bwd: torch.Tensor,
+                           pair_mask_fwd_splits: List[torch.Tensor],
+                           pair_mask_bwd_splits: List[torch.Tensor],
+                           mask_argsort_fwd_splits: List[torch.Tensor],
+                           mask_argsort_bwd_splits: List[torch.Tensor],
+                           mask_output_fwd: Optional[torch.Tensor], masks: List[np.ndarray],
+                           mask_width: int, is_subm: bool,
+                           timer: CUDAKernelTimer = CUDAKernelTimer(False),
+                           fp32_accum: Optional[bool] = None):
+    """Input gradient + weight gradient of the masked implicit GEMM -> ``(din, dfilters)``
+    (``ops.py:1667-1681`` / ``convops.py:2247-2440``)."""
+    _require_cuda(features, "features")
+    lib = _lib()
+    features = features.contiguous()
+    filters = filters.contiguous()
+    out_bp = out_bp.contiguous()
+    if out_bp.dtype != features.dtype:
+        out_bp = out_bp.to(features.dtype)
+    kv, c_in, c_out = _check_filter(features, filters)
+    n_in, n_out = features.shape[0], out_bp.shape[0]
+    din = torch.empty_like(features)
+    dfilters = torch.empty_like(filters)
+    mask_fwd, argsort_fwd = _first(pair_mask_fwd_splits), _first(mask_argsort_fwd_splits)
+    if is_subm:
+        # SubM pairs are symmetric: walk the FORWARD table/mask and flip the filter offset
+        # (the reference's reverse_mask, convops.py:2412)
+        d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask_fwd, argsort_fwd,
+                     reverse=True)
+    else:
+        d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_bwd,
+                     _first(pair_mask_bwd_splits), _first(mask_argsort_bwd_splits))
+    with timer.record("implicit_gemm_dgrad", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_dgrad(ctypes.byref(d_dg), _ptr(out_bp), _ptr(filters),
+                                                _ptr(din), _stream()), "implicit_gemm_dgrad")
+    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask_fwd, argsort_fwd)
+    ws_bytes = lib.spx_implicit_gemm_wgrad_workspace_size(ctypes.byref(d_wg))
+    ws = _bytes(ws_bytes, features.device)
+    with timer.record("implicit_gemm_wgrad", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
+                                                _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                                                _stream()), "implicit_gemm_wgrad")
+    return din, dfilters
+
+
+# ---------------------------------------------------------------------------- ConvAlgo.Native
+def _native_tables(indice_pairs, indice_pair_num, n_in, n_out, kv, subm, inverse, need_fwd,
+                   need_bwd):
+    """compact pairs [2, kv, L] -> dense gather tables + row masks (visited in natural order)."""
+    lib = _lib()
+    dev = indice_pairs.device
+    words = (kv + 31) // 32
+    t_fwd = torch.empty((kv, n_out), dtype=torch.int32, device=dev) if need_fwd else None
+    m_fwd = torch.empty((n_out, words), dtype=torch.int32, device=dev) if need_fwd else None
+    t_bwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev) if need_bwd else None
+    m_bwd = torch.empty((n_in, words), dtype=torch.int32, device=dev) if need_bwd else None
+    _cabi.check(lib.spx_pairs_to_table(_ptr(indice_pairs), _ptr(indice_pair_num), kv,
+                                       int(indice_pairs.shape[2]), n_in, n_out, int(subm),
+                                       int(inverse), _ptr(t_fwd), _ptr(t_bwd), _ptr(m_fwd),
+                                       _ptr(m_bwd), _stream()), "pairs_to_table")
+    return t_fwd, m_fwd, t_bwd, m_bwd
+
+
+def indice_conv(features: torch.Tensor, filters: torch.Tensor, indice_pairs: torch.Tensor,
+                indice_pair_num: torch.Tensor, num_activate_out: int, inverse: bool = False,
+                subm: bool = False, algo: ConvAlgo = ConvAlgo.Native,
+                timer: CUDAKernelTimer = CUDAKernelTimer(False),
+                bias: Optional[torch.Tensor] = None, act_alpha: float = 0.0,
+                act_beta: float = 0.0, act_type=Activation.None_):
+    """Gather-GEMM-scatter forward over a compact rulebook (``ops.py:811-823`` /
+    ``convops.py:1504-1747``).  The compact pairs are scattered into a dense gather table on the
+    device (no ``indice_pair_num.cpu()`` sync) and the output-stationary implicit-GEMM kernel
+    accumulates every offset in TMEM -- no atomics, deterministic."""
+    _require_cuda(features, "features")
+    lib = _lib()
+    features = features.contiguous()
+    filters = filters.contiguous()
+    indice_pairs = indice_pairs.contiguous()
+    kv, c_in, c_out = _check_filter(features, filters)
+    assert features.shape[1] == c_in, "channel size mismatch"
+    assert indice_pairs.shape[1] == kv, "indice_pairs / filter kernel volume mismatch"
+    n_in, n_out = features.shape[0], int(num_activate_out)
+    with timer.record("indice_conv_table", _stream()):
+        t_fwd, m_fwd, _, _ = _native_tables(indice_pairs, indice_pair_num, n_in, n_out, kv, subm,
+                                            inverse, True, False)
+    out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
+    if bias is not None:
+        bias = bias.to(features.dtype).contiguous()
+    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None)
+    with timer.record("indice_conv", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_fwd(ctypes.byref(d), _ptr(features), _ptr(filters),
+                                              _ptr(out), _ptr(bias), _act_code(act_type),
+                                              float(act_alpha), None, _stream()),
+                    "implicit_gemm_fwd(native)")
+    return out
+
+
+def indice_conv_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: torch.Tensor,
+                         indice_pairs: torch.Tensor, indice_pair_num: torch.Tensor,
+                         inverse: bool = False, subm: bool = False,
+                         algo: ConvAlgo = ConvAlgo.Native,
+                         timer: CUDAKernelTimer = CUDAKernelTimer(False)):
+    """Backward of :func:`indice_conv` -> ``(din, dfilters)`` (``ops.py:1103-1111`` /
+    ``convops.py:1751-2071``)."""
+    _require_cuda(features, "features")
+    lib = _lib()
+    features = features.contiguous()
+    filters = filters.contiguous()
+    out_bp = out_bp.contiguous()
+    if out_bp.dtype != features.dtype:
+        out_bp = out_bp.to(features.dtype)
+    indice_pairs = indice_pairs.contiguous()
+    kv, c_in, c_out = _check_filter(features, filters)
+    n_in, n_out = features.shape[0], out_bp.shape[0]
+    t_fwd, m_fwd, t_bwd, m_bwd = _native_tables(indice_pairs, indice_pair_num, n_in, n_out, kv,
+                                                subm, inverse, True, True)
+    din = torch.empty_like(features)
+    dfilters = torch.empty_like(filters)
+    d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_bwd, m_bwd, None)
+    with timer.record("indice_conv_dgrad", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_dgrad(ctypes.byref(d_dg), _ptr(out_bp), _ptr(filters),
+                                                _ptr(din), _stream()), "implicit_gemm_dgrad(native)")
+    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None)
+    ws = _bytes(lib.spx_implicit_gemm_wgrad_workspace_size(ctypes.byref(d_wg)), features.device)
+    with timer.record("indice_conv_wgrad", _stream()):
+        _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
+                                                _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                                                _stream()), "implicit_gemm_wgrad(native)")
+    return din, dfilters
+
+
+# ---------------------------------------------------------------------------- misc
+def bias_add_act_inplace(x: torch.Tensor, bias: Optional[torch.Tensor], act_type=Activation.None_,
+                         act_alpha: float = 0.0, act_beta: float = 0.0) -> torch.Tensor:
+    """``InferenceOps.bias_add_act_inplace`` (``inference.py:166-252``)."""
+    _require_cuda(x, "x")
+    assert x.is_contiguous() and x.dim() == 2
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    _cabi.check(_lib().spx_bias_act_inplace(_ptr(x), _ptr(bias), x.shape[0], x.shape[1],
+                                            _DTYPE_CODE[x.dtype], _act_code(act_type),
+                                            float(act_alpha), _stream()), "bias_act_inplace")
+    return x
+
+
+def maximum_value_int_(ten: torch.Tensor, value: int):
+    """running max of the active-voxel count (``ops.py`` maximum_value_int_)."""
+    ten.clamp_(min=int(value))
+    return ten
+
+
+def last_kernel_family() -> int:
+    """0 none, 1 generic FMA kernels, 2 tcgen05 kernels (what served the last GEMM call)."""
+    return int(_lib().spx_last_kernel_family())
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib().spx_launch_count(int(reset)))
