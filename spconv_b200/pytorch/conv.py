@@ -324,7 +324,7 @@ class SparseConvolution(SparseModule):
                     output_dtype=weight.dtype if output_scale is None else None)
 
         if bias_train is not None:
-            out_features = out_features + bias_train
+            out_features = out_features + bias_train.to(out_features.dtype)
         if not self.subm and not self.inverse and self.record_voxel_count:
             if hasattr(self, _MAX_NUM_VOXELS_DURING_TRAINING):
                 ops.maximum_value_int_(getattr(self, _MAX_NUM_VOXELS_DURING_TRAINING),

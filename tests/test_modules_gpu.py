@@ -1,0 +1,145 @@
+"""Module-level GPU tests: the reference's dense-equivalence test (test/test_conv.py:247-357)
+run through SparseConv3d / SubMConv3d with autograd, against the committed torch golden vectors
+and against live torch conv3d; indice_key caching; inverse conv; AMP."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import random_cloud, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("algo_name", ["Native", "MaskImplicitGemm"])
+@pytest.mark.parametrize("tag,k,s,p,d", [("k3s2p1d1", 3, 2, 1, 1), ("k3s1p1d1", 3, 1, 1, 1),
+                                         ("k2s2p0d1", 2, 2, 0, 1)])
+def test_sparse_conv3d_equals_dense_golden(tag, k, s, p, d, algo_name, cuda_dev):
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.core import ConvAlgo
+    g = np.load(os.path.join(GOLD, "dense_conv_case.npz"))
+    inds, feats, shape = g["inds"], g["feats"], [int(v) for v in g["shape"]]
+    w, y, dy = g[f"{tag}_w"], g[f"{tag}_y"], g[f"{tag}_dy"]
+    C, K = feats.shape[1], w.shape[0]
+    layer = spconv.SparseConv3d(C, K, k, s, p, d, bias=False, algo=ConvAlgo[algo_name]).to(cuda_dev)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(w))
+    x_feats = torch.from_numpy(feats).to(cuda_dev).requires_grad_(True)
+    x = spconv.SparseConvTensor(x_feats, torch.from_numpy(inds).to(cuda_dev), shape, 2)
+    out = layer(x)
+    dense = out.dense()
+    assert tuple(dense.shape) == y.shape
+    assert np.abs(dense.detach().cpu().numpy() - y).max() < 1e-4            # test_conv.py:330
+    dense.backward(torch.from_numpy(dy).to(cuda_dev))
+    # reference gradients: dense conv with dy masked to the active outputs
+    oi = out.indices.long().cpu()
+    dd = torch.zeros((2, C, *shape))
+    dd[inds[:, 0], :, inds[:, 1], inds[:, 2], inds[:, 3]] = torch.from_numpy(feats)
+    dd.requires_grad_(True)
+    wt = torch.from_numpy(w).permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    yy = torch.nn.functional.conv3d(dd, wt, stride=s, padding=p, dilation=d)
+    mask = torch.zeros_like(yy)
+    mask[oi[:, 0], :, oi[:, 1], oi[:, 2], oi[:, 3]] = 1
+    yy.backward(torch.from_numpy(dy) * mask)
+    ref_dw = wt.grad.permute(0, 2, 3, 4, 1).numpy()
+    ref_dx = dd.grad[inds[:, 0], :, inds[:, 1], inds[:, 2], inds[:, 3]].numpy()
+    assert np.abs(layer.weight.grad.cpu().numpy() - ref_dw).max() < 1e-3
+    assert np.abs(x_feats.grad.cpu().numpy() - ref_dx).max() < 1e-4
+
+
+@pytest.mark.parametrize("algo_name", ["Native", "MaskImplicitGemm"])
+def test_subm_equals_dense_on_active_set(algo_name, cuda_dev):
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.core import ConvAlgo
+    rng = np.random.default_rng(484)
+    shape = [19, 18, 17]
+    feats, inds = random_cloud(rng, shape, [1500, 1500], 32)
+    layer = spconv.SubMConv3d(32, 48, 3, dilation=2, bias=True, algo=ConvAlgo[algo_name]).to(cuda_dev)
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev), torch.from_numpy(inds).to(cuda_dev), shape, 2)
+    out = layer(x)
+    assert out.indices is x.indices and out.spatial_shape == shape
+    dense_in = x.dense().cpu()
+    w = layer.weight.detach().cpu().permute(0, 4, 1, 2, 3).contiguous()
+    ref = torch.nn.functional.conv3d(dense_in, w, layer.bias.detach().cpu(), padding=2, dilation=2)
+    ref_rows = ref[inds[:, 0], :, inds[:, 1], inds[:, 2], inds[:, 3]]
+    assert (out.features.cpu() - ref_rows).abs().max() < 1e-4
+
+
+def test_indice_key_reuse_and_errors(cuda_dev):
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(1)
+    shape = [24, 24, 24]
+    feats, inds = random_cloud(rng, shape, [2500], 16)
+    net = spconv.SparseSequential(
+        spconv.SubMConv3d(16, 16, 3, indice_key="subm1"), torch.nn.ReLU(),
+        spconv.SubMConv3d(16, 16, 3, indice_key="subm1"), torch.nn.ReLU(),
+        spconv.SparseConv3d(16, 32, 3, 2, 1, indice_key="down1"),
+        spconv.SubMConv3d(32, 32, 3, indice_key="subm2"),
+        spconv.SparseInverseConv3d(32, 16, 3, indice_key="down1"),
+    ).to(cuda_dev).half()
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev).half(), torch.from_numpy(inds).to(cuda_dev), shape, 1)
+    ops.launch_count(reset=True)
+    y = net(x)
+    assert set(y.indice_dict) == {"subm1", "down1", "subm2"}
+    # the second subm1 layer reuses the cached rulebook; the inverse conv restores the input set
+    assert y.indices.shape == x.indices.shape and torch.equal(y.indices, x.indices)
+    assert y.spatial_shape == shape and y.features.shape == (2500, 16)
+    assert torch.isfinite(y.features.float()).all()
+    # same key, different kernel size -> reference error text
+    bad = spconv.SubMConv3d(16, 16, 5, indice_key="subm1").to(cuda_dev).half()
+    with pytest.raises(ValueError, match="same kernel size"):
+        bad(net[0](x))
+    # a regular conv cannot reuse a key
+    dup = spconv.SparseConv3d(16, 16, 3, 2, 1, indice_key="down1").to(cuda_dev).half()
+    with pytest.raises(AssertionError, match="only support reuse subm indices"):
+        dup(net[4](net[0](x)))
+    # different algo on a shared key
+    from spconv_b200.core import ConvAlgo
+    nat = spconv.SubMConv3d(16, 16, 3, indice_key="subm1", algo=ConvAlgo.Native).to(cuda_dev).half()
+    with pytest.raises(AssertionError, match="same algo"):
+        nat(net[0](x))
+
+
+def test_inverse_conv_matches_oracle(oracle, cuda_dev):
+    import spconv_b200.pytorch as spconv
+    rng = np.random.default_rng(2)
+    shape = [20, 20, 20]
+    feats, inds = random_cloud(rng, shape, [1800], 16)
+    down = spconv.SparseConv3d(16, 32, 3, 2, 1, bias=False, indice_key="d").to(cuda_dev)
+    up = spconv.SparseInverseConv3d(32, 16, 3, indice_key="d", bias=False).to(cuda_dev)
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev), torch.from_numpy(inds).to(cuda_dev), shape, 1)
+    mid = down(x)
+    y = up(mid)
+    o, p, n = oracle.get_indice_pairs(inds, 1, shape, [3] * 3, [2] * 3, [1] * 3, [1] * 3, [0] * 3, False)
+    r_mid = oracle.indice_conv(feats, down.weight.detach().cpu().numpy(), p, n, o.shape[0], False, False)
+    r_y = oracle.indice_conv(r_mid, up.weight.detach().cpu().numpy(), p, n, feats.shape[0], True, False)
+    assert np.abs(mid.features.detach().cpu().numpy() - r_mid).max() < 1e-4
+    assert np.abs(y.features.detach().cpu().numpy() - r_y).max() < 1e-3
+
+
+def test_training_step_matches_fp32_oracle_and_amp(oracle, cuda_dev):
+    import spconv_b200.pytorch as spconv
+    rng = np.random.default_rng(3)
+    shape = [24, 24, 24]
+    feats, inds = random_cloud(rng, shape, [3000], 32)
+    layer = spconv.SubMConv3d(32, 64, 3, bias=True).to(cuda_dev)
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev), torch.from_numpy(inds).to(cuda_dev), shape, 1)
+    layer.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = layer(x)                       # custom_fwd casts features and weight to fp16
+    assert y.features.dtype == torch.float16
+    loss = y.features.float().square().mean()
+    loss.backward()
+    _, p, n = oracle.get_indice_pairs(inds, 1, shape, [3] * 3, [1] * 3, [1] * 3, [1] * 3, [0] * 3, True)
+    w = layer.weight.detach().half().float().cpu().numpy()
+    f16 = torch.from_numpy(feats).half().float().numpy()
+    ref = oracle.indice_conv(f16, w, p, n, 3000, False, True) + layer.bias.detach().cpu().numpy()
+    assert rel_l2(y.features.float().detach().cpu().numpy(), ref) < 1e-2
+    assert layer.weight.grad is not None and layer.weight.grad.dtype == torch.float32
+    assert layer.bias.grad is not None
+    dout = (2.0 / ref.size) * ref
+    _, ref_dw = oracle.indice_conv_backward(f16, w, dout, p, n, False, True)
+    assert rel_l2(layer.weight.grad.cpu().numpy(), ref_dw) < 3e-2
