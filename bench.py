@@ -74,6 +74,23 @@ def cpu_reference_step(orc, inds, feats, w, dout, wl):
     return {"rulebook_s": t1 - t0, "fwd_s": t2 - t1, "bwd_s": t3 - t2, "total_s": t3 - t0, "n": inds.shape[0]}
 
 
+CPU_THREAD_CAP = 16     # the small per-offset GEMMs get SLOWER with more BLAS threads (measured: 128 -> 3.2 s/step)
+
+
+def cpu_threads() -> int:
+    return min(os.cpu_count() or 1, CPU_THREAD_CAP)
+
+
+def limit_blas_threads():
+    """The reference's CPU path runs its per-offset mm on the host BLAS; give it the thread count
+    where it is fastest on this box instead of oversubscribing every core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cpu_threads())
+    except Exception:
+        pass
+
+
 def make_cpu_sample(wl, n, seed):
     rng = np.random.default_rng(seed)
     scale = max(n / wl["n"], 1e-3) ** 0.5
@@ -93,6 +110,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     orc.build()
+    limit_blas_threads()
     wl = WORKLOADS[args.workload]
     inds, feats, w, dout, wl_s = make_cpu_sample(wl, args.cpu_sample, 1234)
     for _ in range(min(args.warmup, 2)):
@@ -106,7 +124,7 @@ def run_reference(args):
     tot = sum(r["total_s"] for r in recs)
     steps = len(recs)
     value = inds.shape[0] * steps / tot
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     sample = (f"{inds.shape[0]} voxels of the same generator in a {wl_s['shape']} grid, fp32, "
               f"single-threaded rulebook + numpy/BLAS gather-mm-scatter fwd+bwd")
     line = {
@@ -265,12 +283,17 @@ def run_ours(args):
         e2e_step(i)
     torch.cuda.synchronize()
 
+    # kernels of THIS library per step (graph replays re-issue exactly the captured launches)
+    ops.launch_count(reset=True)
+    device_step(clouds[0])
+    launches_per_step = ops.launch_count(reset=True)
+    torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.launch_count(reset=True)
     ms_value = timed_loop(value_step, args.steps)
-    launches = ops.launch_count(reset=True)
+    launches = launches_per_step * args.steps
     ms_e2e = timed_loop(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
 
@@ -311,6 +334,7 @@ def run_ours(args):
         from oracle import oracle as orc
         orc.build()
         s_inds, s_feats, s_w, s_dout, wl_s = make_cpu_sample(wl, args.cpu_sample, 1234)
+        limit_blas_threads()
         cpu_reference_step(orc, s_inds[:2000], s_feats[:2000], s_w, s_dout, wl_s)     # warm BLAS
         recs, t0 = [], time.perf_counter()
         while len(recs) < 3 or (time.perf_counter() - t0 < 10 and len(recs) < 20):
@@ -347,7 +371,7 @@ def run_ours(args):
                          "tensor_tflops_fwd": flops / (regions.get("implicit_gemm", float("nan")) * 1e-3) / 1e12,
                          "tensor_frac_fwd": flops / (regions.get("implicit_gemm", float("nan")) * 1e-3) / 1e12
                          / peaks["bf16_tflops"]},
-            "cpu_baseline": {"value": cpu_value, "unit": "voxels/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "cpu_baseline": {"value": cpu_value, "unit": "voxels/s", "cores": cpu_threads(), "kind": "port",
                              "sample": sample,
                              "rulebook_ms": 1e3 * sum(r["rulebook_s"] for r in recs) / len(recs),
                              "fwd_ms": 1e3 * sum(r["fwd_s"] for r in recs) / len(recs),

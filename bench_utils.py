@@ -23,21 +23,23 @@ def surface_cloud(rng: np.random.Generator, shape, n_target: int, batch: int = 1
     D, H, W = [int(s) for s in shape]
     out = []
     for b in range(batch):
-        keys = np.empty((0,), np.int64)
-        while keys.shape[0] < n_target:
-            new = []
-            for _ in range(64):
-                cz, cy, cx = rng.integers(0, D), rng.integers(0, H), rng.integers(0, W)
-                ext = int(rng.integers(8, 40))
-                sy, sx = rng.uniform(-0.3, 0.3, size=2)
-                ys = np.arange(max(0, cy - ext), min(H, cy + ext))
-                xs = np.arange(max(0, cx - ext), min(W, cx + ext))
-                yy, xx = np.meshgrid(ys, xs, indexing="ij")
-                zz = np.clip(np.round(cz + sy * (yy - cy) + sx * (xx - cx)).astype(np.int64), 0, D - 1)
-                sel = rng.random(yy.shape) < keep
-                new.append((zz[sel] * H + yy[sel]) * W + xx[sel])
-            keys = np.unique(np.concatenate([keys, *new]))
-        keys = keys[rng.permutation(keys.shape[0])[:n_target]]
+        seen = np.empty((0,), np.int64)
+        while seen.shape[0] < n_target:
+            cz, cy, cx = rng.integers(0, D), rng.integers(0, H), rng.integers(0, W)
+            ext = int(rng.integers(8, 40))
+            sy, sx = rng.uniform(-0.3, 0.3, size=2)
+            ys = np.arange(max(0, cy - ext), min(H, cy + ext))
+            xs = np.arange(max(0, cx - ext), min(W, cx + ext))
+            yy, xx = np.meshgrid(ys, xs, indexing="ij")
+            zz = np.clip(np.round(cz + sy * (yy - cy) + sx * (xx - cx)).astype(np.int64), 0, D - 1)
+            sel = rng.random(yy.shape) < keep
+            patch = np.unique((zz[sel] * H + yy[sel]) * W + xx[sel])
+            patch = patch[~np.isin(patch, seen)]
+            room = n_target - seen.shape[0]
+            if patch.shape[0] > room:                 # truncate the last patch, keep whole rows of it
+                patch = patch[:room]
+            seen = np.concatenate([seen, patch])
+        keys = seen[rng.permutation(seen.shape[0])]
         z, rem = np.divmod(keys, H * W)
         y, x = np.divmod(rem, W)
         out.append(np.stack([np.full_like(z, b), z, y, x], axis=1).astype(np.int32))

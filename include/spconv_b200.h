@@ -153,7 +153,27 @@ typedef struct {
     int reverse_offsets;        /* 1: offset k of `pair`/`mask` multiplies filter kv-1-k
                                    (SubM dgrad through the forward table; reference
                                    reverse_mask, spconv/csrc/sparse/convops.py:2412) */
+    const int32_t *tile_table;  /* optional: spx_build_tile_table output for (pair, argsort);  */
+    const uint32_t *tile_mask;  /* both or neither.  Required by the tcgen05 kernels: without   */
+                                /* them the call runs on the generic FMA kernels.               */
 } spx_gemm_desc;
+
+/*
+ * Tile-blocked gather table: the (pair, argsort, mask) triple re-laid so that one 128-row tile is
+ * one contiguous block the kernels fetch with a single bulk async copy:
+ *   table     [tiles][kv + 1][128] int32:  table[t][k][r] = pair[k][row(t*128 + r)]  (k < kv),
+ *                                          table[t][kv][r] = row(t*128 + r)   (-1 past the end)
+ *             with row(j) = argsort ? argsort[j] : j
+ *   tile_mask [tiles][words] uint32: OR of mask[t*128 .. t*128+127] (mask in visiting order;
+ *             NULL mask = all kv offsets) == the reference's mask_output_fwd with mask_width 128
+ *             (spconv/csrc/sparse/convops.py:2180-2189)
+ * tiles = ceil(rows / 128).  Built once per rulebook, shared by fwd / dgrad / wgrad of every
+ * layer that shares the indice_key.
+ */
+size_t spx_tile_table_elems(int64_t rows, int kv);
+int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, int kv, const int32_t *argsort,
+                         const uint32_t *mask, int64_t rows, int32_t *table, uint32_t *tile_mask,
+                         spx_stream_t stream);
 
 /*
  * out[o, :] = act( sum_k x[pair[k][o], :] @ W[:, k, :]^T  + bias )      rows = n_out

@@ -37,6 +37,7 @@ class GemmDesc(Structure):
         ("pair", c_void_p), ("pair_stride", c_int64),
         ("mask", c_void_p), ("argsort", c_void_p),
         ("reverse_offsets", c_int),
+        ("tile_table", c_void_p), ("tile_mask", c_void_p),
     ]
 
 
@@ -62,6 +63,9 @@ SIGNATURES = {
     "spx_mask_argsort_workspace_size": (c_size_t, [c_int64, c_int]),
     "spx_mask_argsort": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                  c_size_t, c_void_p]),
+    "spx_tile_table_elems": (c_size_t, [c_int64, c_int]),
+    "spx_build_tile_table": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                     c_void_p, c_void_p]),
     "spx_implicit_gemm_fwd": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_float, c_void_p, c_void_p]),
     "spx_implicit_gemm_dgrad": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p,

@@ -26,6 +26,7 @@ static int check_desc(const spx_gemm_desc *d, const char *who) {
     SPX_REQUIRE(d->n_in >= 0 && d->n_out >= 0, "%s: negative row counts", who);
     SPX_REQUIRE(d->n_in < 2147483647ll && d->n_out < 2147483647ll, "%s: row counts must fit in int32", who);
     SPX_REQUIRE(d->pair != nullptr || (d->n_in == 0 || d->n_out == 0), "%s: pair table is NULL", who);
+    SPX_REQUIRE((d->tile_table == nullptr) == (d->tile_mask == nullptr), "%s: tile_table and tile_mask go together", who);
     return 0;
 }
 
@@ -39,6 +40,7 @@ static GatherGemmArgs make_args(const spx_gemm_desc *d, bool dgrad) {
     a.x_rows = dgrad ? d->n_out : d->n_in;
     a.pair = d->pair; a.pair_stride = d->pair_stride;
     a.mask = d->mask; a.argsort = d->argsort;
+    a.tile_table = d->tile_table; a.tile_mask = d->tile_mask;
     return a;
 }
 
@@ -88,6 +90,7 @@ static WgradArgs make_wgrad(const spx_gemm_desc *d) {
     w.dtype = d->dtype; w.f32_mode = d->f32_mode; w.kv = d->kv; w.c_in = d->c_in; w.c_out = d->c_out;
     w.n_in = d->n_in; w.n_out = d->n_out;
     w.pair = d->pair; w.pair_stride = d->pair_stride; w.mask = d->mask; w.argsort = d->argsort;
+    w.tile_table = d->tile_table; w.tile_mask = d->tile_mask;
     return w;
 }
 

@@ -154,6 +154,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
         "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// 1-D bulk async copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -233,6 +238,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= 1ull << 46;                 // descriptor version (Blackwell)
     d |= layout << 61;
     return d;
+}
+
+// Constant (address-independent) part of a descriptor; OR it with ((smem_addr >> 4) & 0x3FFF).
+__host__ __device__ __forceinline__ uint64_t smem_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle_bytes) {
+    uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : (swizzle_bytes == 32 ? 6ull : 0ull));
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (layout << 61);
 }
 
 // Instruction descriptor, dense, no negate, no saturate.

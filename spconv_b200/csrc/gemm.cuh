@@ -22,6 +22,8 @@ struct GatherGemmArgs {
     const uint32_t *mask;      // [rows, words] in visiting order, or NULL
     const int32_t *argsort;    // [rows] or NULL
     uint32_t *mask_out;        // [ceil(rows/128), words] or NULL
+    const int32_t *tile_table; // [tiles][kv+1][128] or NULL (spx_build_tile_table)
+    const uint32_t *tile_mask; // [tiles][words] or NULL
     __host__ __device__ int cx() const { return transpose_w ? c_out : c_in; }
     __host__ __device__ int cy() const { return transpose_w ? c_in : c_out; }
 };
@@ -36,6 +38,8 @@ struct WgradArgs {
     int64_t pair_stride;
     const uint32_t *mask;      // [n_out, words] in visiting order or NULL
     const int32_t *argsort;    // [n_out] or NULL
+    const int32_t *tile_table; // [tiles][kv+1][128] or NULL
+    const uint32_t *tile_mask; // [tiles][words] or NULL
     void *workspace;
     size_t workspace_bytes;
 };

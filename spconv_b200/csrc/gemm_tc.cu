@@ -1,12 +1,15 @@
 // tcgen05 / TMEM / TMA masked implicit GEMM: forward and input-gradient (and int8 forward).
 //
-// One persistent CTA per SM walks 128-row output tiles (rows in mask_argsort order).  For each
-// kernel offset whose bit is set in the OR of the tile's neighbour masks:
-//   * 4 producer warps gather the 128 input rows named by the pair table into a swizzled
-//     K-major shared-memory tile with 16-byte cp.async (zero-fill for "-1 = no neighbour"),
-//   * one lane TMA-loads that offset's KRSC weight slice W[:, k, :] (a strided 2-D box),
+// One persistent CTA per SM walks 128-row output tiles (rows in mask_argsort order).  Per tile
+// the gather indices arrive as ONE bulk async copy (cp.async.bulk) of the tile's block of the
+// tile table (spx_build_tile_table), prefetched a tile ahead.  For each kernel offset whose bit
+// is set in the tile's OR-mask:
+//   * 4 producer warps gather the 128 input rows into a swizzled K-major shared-memory tile with
+//     16-byte cp.async (zero-fill for "-1 = no neighbour"); all per-lane addressing is hoisted
+//     out of the pipeline (compile-time chunk count CPR), ~6 instructions per 16-byte copy;
+//   * one lane TMA-loads that offset's KRSC weight slice W[:, k, :] (a strided 2-D box);
 //   * one lane issues tcgen05.mma (M = 128, N = out channels, K = 32 bytes per instruction)
-//     accumulating the whole offset sum in TMEM,
+//     accumulating the whole offset sum in TMEM;
 // and 4 epilogue warps drain the previous tile's accumulator (tcgen05.ld -> bias/act ->
 // vectorised row stores) while the next tile is being multiplied (two TMEM accumulators).
 //
@@ -31,23 +34,23 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 struct TcParams {
     // gathered operand A
     const uint8_t *x;
-    int xb;                 // bytes per gathered row (contraction length in bytes)
-    int span_a;             // swizzle span of A sub-tiles: min(128, xb)
-    int ksteps;             // xb / 32
+    int xb;                 // bytes per gathered row (contraction length in bytes) = CPR * 16
+    int span_a, lg_span_a;  // swizzle span of A sub-tiles: min(128, xb)
+    int a_subtiles;         // xb / span_a
+    int q_a;                // k-steps (32 B) per A sub-tile = span_a / 32
     // weight operand B (TMA box = [b_rows x span_b bytes] per sub-tile)
-    int span_b, b_subtiles, b_rows, b_sub_bytes, b_bytes, b_mn_major, umma_k_rows;
+    int span_b, b_subtiles, b_sub_bytes, b_bytes, b_mn_major, q_b, b_kstep16_mn;
     int w_inner_elems;      // c_in (elements between consecutive offsets along the TMA inner dim)
     int span_b_elems;       // span_b / elem bytes
     int n;                  // UMMA N (output channels of this pass)
     uint32_t idesc;
-    int stages, a_stage_bytes, stage_bytes;
+    int stages, a_stage_bytes, stage_bytes, idx_bytes;
     uint32_t tmem_cols;
     // rows
     int64_t rows;
-    const int32_t *pair;
-    int64_t pair_stride;
-    const uint32_t *mask;
-    const int32_t *argsort;
+    const int32_t *tile_table;   // [tiles][kv+1][128]
+    const uint32_t *tile_mask;   // [tiles][words]
+    const int32_t *argsort;      // destination rows of the epilogue (NULL = identity)
     int kv, words, reverse;
     // epilogue
     void *y;
@@ -58,7 +61,6 @@ struct TcParams {
     const float *scale, *bias_f32;
     const int8_t *output_add;
     float output_add_scale;
-    uint32_t *mask_out;
 };
 
 // iterate set bits of a <=128-bit tile mask in ascending order
@@ -78,35 +80,120 @@ struct BitIter {
     }
 };
 
-// OR of the visiting-order masks of rows [base, base+128); all lanes get the result
-__device__ __forceinline__ void tile_mask_or(const uint32_t *__restrict__ mask, int64_t base, int64_t rows, int words,
-                                             int kv, int lane, uint32_t (&out)[4]) {
-    bool any = false;
+// per-tile offset set (warp-uniform); an all-zero mask still runs offset 0 (all rows "-1" -> zeros)
+__device__ __forceinline__ void load_tile_mask(const uint32_t *__restrict__ tile_mask, int64_t tile, int words,
+                                               uint32_t (&out)[4]) {
+    uint32_t any = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        uint32_t m = 0;
-        if (w < words) {
-            if (mask) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    int64_t row = base + r * 32 + lane;
-                    if (row < rows) m |= __ldg(mask + row * words + w);
-                }
-                m = __reduce_or_sync(0xffffffffu, m);
-            } else {
-                int hi = kv - 32 * w;
-                m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
-            }
-        }
-        out[w] = m;
-        any = any || m != 0;
+        out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
+        any |= out[w];
     }
-    if (!any) out[0] = 1u;   // keep the pipeline uniform: offset 0 with all rows "-1" -> zeros
+    if (!any) out[0] = 1u;
 }
 
-template <int KIND>
+// ------------------------------------------------------------------ epilogue, one row per thread
+// 16 accumulator columns -> OUT type, 16-byte vector stores.  OUT is an spx_dtype code.
+template <int OUT>
+__device__ __forceinline__ void store16(uint8_t *dst, const float (&f)[16]) {
+    if constexpr (OUT == SPX_F32) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4 *>(dst + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else if constexpr (OUT == SPX_F16) {
+        uint32_t h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            h[j] = *reinterpret_cast<uint32_t *>(&t);
+        }
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+    } else if constexpr (OUT == SPX_BF16) {
+        uint32_t h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            h[j] = *reinterpret_cast<uint32_t *>(&t);
+        }
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+    } else {   // int8: clip(rint(.)) -- numpy round-half-even
+        uint32_t q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float r = fminf(fmaxf(rintf(f[4 * j + b]), -128.f), 127.f);
+                w |= ((uint32_t)(uint8_t)(int8_t)(int)r) << (8 * b);
+            }
+            q[j] = w;
+        }
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+}
+
+template <int OUT> struct OutElem { static constexpr int bytes = OUT == SPX_F32 ? 4 : (OUT == SPX_I8 ? 1 : 2); };
+
+template <int OUT>
+__device__ __forceinline__ float load_bias(const void *bias, int j) {
+    if constexpr (OUT == SPX_F32) return ((const float *)bias)[j];
+    else if constexpr (OUT == SPX_F16) return __half2float(((const __half *)bias)[j]);
+    else return __bfloat162float(((const __nv_bfloat16 *)bias)[j]);
+}
+
+// drain one accumulator (this warp's 32 TMEM lanes x n columns) to global memory
+template <int OUT, bool INT8_MODE>
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t t_row, int64_t dst_row) {
+    constexpr int EB = OutElem<OUT>::bytes;
+    uint8_t *row_ptr = (uint8_t *)p.y + dst_row * (int64_t)p.n * EB;
+    const bool has_bias = INT8_MODE ? (p.bias_f32 != nullptr) : (p.bias != nullptr);
+    for (int n0 = 0; n0 < p.n; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + (uint32_t)n0, v);
+        tc_wait_ld();
+        if (dst_row < 0) continue;
+        float f[16];
+        if constexpr (!INT8_MODE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (has_bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += load_bias<OUT == SPX_I8 ? SPX_F32 : OUT>(p.bias, n0 + j);
+            }
+        } else {
+            // int8 inference: y = acc * scale[k] + bias[k] (+ add * add_scale)   test/test_all_algo.py:272-287
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = (float)(int32_t)v[j] * __ldg(p.scale + n0 + j);
+            if (has_bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias_f32 + n0 + j);
+            }
+            if (p.output_add) {
+                const int8_t *ap = p.output_add + dst_row * (int64_t)p.n + n0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += (float)ap[j] * p.output_add_scale;
+            }
+        }
+        if (p.act != SPX_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act, p.alpha);
+        }
+        store16<OUT>(row_ptr + n0 * EB, f);
+    }
+}
+
+template <int KIND, int CPR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+    constexpr int LG_CPR = CPR == 2 ? 1 : CPR == 4 ? 2 : CPR == 8 ? 3 : CPR == 16 ? 4 : 5;
+    constexpr int RPI = 32 / CPR;            // rows covered by one warp-wide cp.async instruction
+    constexpr int XB = CPR * 16;             // bytes per gathered row
+    constexpr int SPAN_A = XB < 128 ? XB : 128;
+    constexpr int LG_SPAN_A = SPAN_A == 128 ? 7 : (SPAN_A == 64 ? 6 : 5);
+    constexpr int A_SUB_BYTES = TC_TILE_M * SPAN_A;
+
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: align manually to 1024
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -114,12 +201,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     uint8_t *smem = smem_raw + pad;
     const uint32_t smem_base = raw_addr + pad;
 
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes);
-    uint64_t *full = bars;                         // [stages]  producers + TMA -> MMA
-    uint64_t *empty = bars + TC_MAX_STAGES;        // [stages]  MMA -> producers
-    uint64_t *tmem_full = bars + 2 * TC_MAX_STAGES;      // [2] MMA -> epilogue
-    uint64_t *tmem_empty = bars + 2 * TC_MAX_STAGES + 2; // [2] epilogue -> MMA
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 4);
+    const uint32_t idx_off = (uint32_t)p.stages * p.stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + idx_off + 2u * p.idx_bytes);
+    uint64_t *full = bars;                                // [stages]  producers + TMA -> MMA
+    uint64_t *empty = bars + TC_MAX_STAGES;               // [stages]  MMA -> producers
+    uint64_t *tmem_full = bars + 2 * TC_MAX_STAGES;       // [2] MMA -> epilogue
+    uint64_t *tmem_empty = bars + 2 * TC_MAX_STAGES + 2;  // [2] epilogue -> MMA
+    uint64_t *idx_full = bars + 2 * TC_MAX_STAGES + 4;    // [2] bulk copy -> producers
+    uint64_t *idx_empty = bars + 2 * TC_MAX_STAGES + 6;   // [2] producers -> bulk copy
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -133,6 +223,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
+            mbar_init(&idx_full[a], 1);      // expect_tx arrival of the bulk copy
+            mbar_init(&idx_empty[a], 128);   // every producer thread releases the buffer
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap_w);
@@ -150,41 +242,61 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     if (warp >= 4 && warp < 8) {
         // ================================================= gather producers
         const int pw = warp - 4;
-        const int cpr = p.xb >> 4;                 // 16-byte chunks per row
+        const bool leader = (pw == 0 && lane == 0);
+        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
+        // per-lane constants: chunk ch of rows r0 + itc*RPI (itc = 0..CPR-1) of this warp's 32 rows
+        const int r0 = lane >> LG_CPR;
+        const uint32_t byte_in_row = (uint32_t)(lane & (CPR - 1)) << 4;
+        const uint8_t *x_lane = p.x + byte_in_row;
+        uint32_t dst_off[CPR];
+#pragma unroll
+        for (int itc = 0; itc < CPR; ++itc) {
+            const uint32_t row_in_tile = (uint32_t)(pw * 32 + r0 + itc * RPI);
+            const uint32_t sub = byte_in_row >> LG_SPAN_A;
+            const uint32_t within = byte_in_row & (uint32_t)(SPAN_A - 1);
+            dst_off[itc] = sub * (uint32_t)A_SUB_BYTES + swizzle_offset((row_in_tile << LG_SPAN_A) + within, SPAN_A);
+        }
         int stage = 0; uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t base = tile * TC_TILE_M;
-            uint32_t tm[4];
-            tile_mask_or(p.mask, base, p.rows, p.words, p.kv, lane, tm);
-            const int64_t my_row = base + pw * 32 + lane;
-            int32_t src_row = -1;
-            if (my_row < p.rows) src_row = p.argsort ? __ldg(p.argsort + my_row) : (int32_t)my_row;
+        int64_t local = 0;
+        int64_t tile = blockIdx.x;
+        // the gather-index block of tile t+1 is bulk-copied while tile t is being gathered
+        auto fetch_indices = [&](int64_t t, int64_t lcl) {
+            const int b = (int)(lcl & 1);
+            const uint32_t use = (uint32_t)(lcl >> 1);
+            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
+            bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
+                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
+        };
+        uint32_t tm[4] = {0, 0, 0, 0};
+        if (tile < num_tiles) {
+            if (leader) fetch_indices(tile, 0);
+            load_tile_mask(p.tile_mask, tile, p.words, tm);
+        }
+        for (; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int buf = (int)(local & 1);
+            const int64_t next = tile + gridDim.x;
+            uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (next < num_tiles) {
+                load_tile_mask(p.tile_mask, next, p.words, tm_next);
+                if (leader) fetch_indices(next, local + 1);
+            }
+            mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
+            const int32_t *idx_lane = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes) +
+                                      pw * 32 + r0;
             BitIter it{{tm[0], tm[1], tm[2], tm[3]}, 0};
-            int k = it.next();
-            int32_t idx = (src_row >= 0) ? __ldg(p.pair + (int64_t)k * p.pair_stride + src_row) : -1;
-            while (k >= 0) {
-                const int kn = it.next();
-                int32_t idx_n = -1;
-                if (kn >= 0 && src_row >= 0) idx_n = __ldg(p.pair + (int64_t)kn * p.pair_stride + src_row);
+            for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&empty[stage], phase ^ 1u);
                 const uint32_t a_stage = smem_base + (uint32_t)stage * p.stage_bytes;
-                // 32 rows x cpr chunks per warp; consecutive lanes take consecutive 16-byte chunks
-                for (int itc = 0; itc < cpr; ++itc) {
-                    const int flat = itc * 32 + lane;
-                    const int r = flat / cpr;
-                    const int ch = flat - r * cpr;
-                    const int32_t ridx = __shfl_sync(0xffffffffu, idx, r);
-                    const uint32_t byte_in_row = (uint32_t)ch << 4;
-                    const uint32_t sub = byte_in_row / (uint32_t)p.span_a;
-                    const uint32_t within = byte_in_row - sub * p.span_a;
-                    const uint32_t row_in_tile = (uint32_t)(pw * 32 + r);
-                    const uint32_t dst = a_stage + sub * (uint32_t)(TC_TILE_M * p.span_a) +
-                                         swizzle_offset(row_in_tile * p.span_a + within, p.span_a);
-                    const uint8_t *src = p.x + (ridx >= 0 ? (int64_t)ridx * p.xb + byte_in_row : 0);
-                    cp_async_16(dst, src, ridx >= 0 ? 16u : 0u);
+                const int32_t *idx_k = idx_lane + k * 128;
+#pragma unroll
+                for (int itc = 0; itc < CPR; ++itc) {
+                    const int32_t ridx = idx_k[itc * RPI];
+                    const uint8_t *src = x_lane + (int64_t)max(ridx, 0) * XB;
+                    cp_async_16(a_stage + dst_off[itc], src, ridx >= 0 ? 16u : 0u);
                 }
                 cp_async_mbar_arrive_noinc(&full[stage]);
-                if (pw == 0 && lane == 0) {
+                if (leader) {
                     const int kw = p.reverse ? p.kv - 1 - k : k;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)p.b_bytes);
                     const uint32_t b_stage = a_stage + p.a_stage_bytes;
@@ -193,62 +305,80 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
                                     kw * p.w_inner_elems + sb * p.span_b_elems, 0);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                k = kn; idx = idx_n;
             }
+            mbar_arrive(&idx_empty[buf]);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
     } else if (warp == 8) {
         // ================================================= MMA issuer
         int stage = 0; uint32_t phase = 0;
         int64_t local = 0;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int64_t base = tile * TC_TILE_M;
-            uint32_t tm[4];
-            tile_mask_or(p.mask, base, p.rows, p.words, p.kv, lane, tm);
-            if (p.mask_out && lane < p.words) p.mask_out[tile * p.words + lane] = tm[lane];
+        int64_t tile = blockIdx.x;
+        uint32_t tm[4] = {0, 0, 0, 0};
+        if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
+        // loop-invariant descriptor pieces (descriptor = high part | (address >> 4))
+        const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
+        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
+                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
+        const uint32_t b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
+        for (; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int64_t next = tile + gridDim.x;
+            uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (next < num_tiles) load_tile_mask(p.tile_mask, next, p.words, tm_next);
             const int acc = (int)(local & 1);
             const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n);
             BitIter it{{tm[0], tm[1], tm[2], tm[3]}, 0};
-            bool first = true;
+            uint32_t accumulate = 0;
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 fence_proxy_async_smem();
                 if (lane == 0) {
-                    const uint32_t a_stage = smem_base + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t b_stage = a_stage + p.a_stage_bytes;
-                    for (int j = 0; j < p.ksteps; ++j) {
-                        const uint32_t kb = (uint32_t)j * 32u;
-                        const uint32_t a_sub = kb / (uint32_t)p.span_a;
-                        const uint32_t a_off = kb - a_sub * p.span_a;
-                        const uint64_t a_desc = make_smem_desc(a_stage + a_sub * (uint32_t)(TC_TILE_M * p.span_a) + a_off,
-                                                               16u, 8u * p.span_a, p.span_a);
-                        uint64_t b_desc;
-                        if (!p.b_mn_major) {
-                            const uint32_t b_sub = kb / (uint32_t)p.span_b;
-                            const uint32_t b_off = kb - b_sub * p.span_b;
-                            b_desc = make_smem_desc(b_stage + b_sub * p.b_sub_bytes + b_off, 16u, 8u * p.span_b, p.span_b);
-                        } else {
-                            b_desc = make_smem_desc(b_stage + (uint32_t)j * p.umma_k_rows * p.span_b,
-                                                    (uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b);
+                    const uint32_t a16 = (smem_base + (uint32_t)stage * p.stage_bytes) >> 4;
+                    const uint32_t b16 = a16 + ((uint32_t)p.a_stage_bytes >> 4);
+                    if (!p.b_mn_major) {
+                        // A and B are both K-major with the same contraction bytes: walk sub-tiles
+                        // (128-byte column blocks), 32 bytes (= 2 x 16 B units) per instruction
+                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
+                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
+                            const uint32_t bs = b16 + (uint32_t)sub * b_sub16;
+                            for (int jr = 0; jr < p.q_a; ++jr) {
+                                umma_ss<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
+                                              b_hi | (uint64_t)((bs + 2u * jr) & 0x3FFFu), p.idesc, accumulate);
+                                accumulate = 1u;
+                            }
                         }
-                        umma_ss<KIND>(d_tmem, a_desc, b_desc, p.idesc, (first && j == 0) ? 0u : 1u);
+                    } else {
+                        // dgrad: B is MN-major, one k-step = umma_k rows of the weight box
+                        int j = 0;
+                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
+                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
+                            for (int jr = 0; jr < p.q_a; ++jr, ++j) {
+                                umma_ss<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
+                                              b_hi | (uint64_t)((b16 + (uint32_t)j * p.b_kstep16_mn) & 0x3FFFu),
+                                              p.idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
                     }
                     tc_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
                 }
                 __syncwarp();
-                first = false;
+                accumulate = 1u;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             if (lane == 0) tc_commit(&tmem_full[acc]);   // accumulator complete
             __syncwarp();
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
     } else {
         // ================================================= epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31)
         int64_t local = 0;
-        const int ybytes = dtype_bytes(p.out_dtype);
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             const int64_t base = tile * TC_TILE_M;
             const int acc = (int)(local & 1);
@@ -259,70 +389,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.n);
-            for (int n0 = 0; n0 < p.n; n0 += 16) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_row + (uint32_t)n0, v);
-                tc_wait_ld();
-                if (dst_row >= 0) {
-                    float f[16];
-                    if (p.epi_mode == 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float val = __uint_as_float(v[j]);
-                            if (p.bias) {
-                                if (p.out_dtype == SPX_F32) val += ((const float *)p.bias)[n0 + j];
-                                else if (p.out_dtype == SPX_F16) val += __half2float(((const __half *)p.bias)[n0 + j]);
-                                else val += __bfloat162float(((const __nv_bfloat16 *)p.bias)[n0 + j]);
-                            }
-                            f[j] = apply_act(val, p.act, p.alpha);
-                        }
-                    } else {
-                        // int8 inference: test/test_all_algo.py:272-287
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float val = (float)(int32_t)v[j] * p.scale[n0 + j] + (p.bias_f32 ? p.bias_f32[n0 + j] : 0.f);
-                            if (p.output_add) val += (float)p.output_add[dst_row * p.n + n0 + j] * p.output_add_scale;
-                            f[j] = apply_act(val, p.act, p.alpha);
-                        }
-                    }
-                    uint8_t *dst = (uint8_t *)p.y + (dst_row * p.n + n0) * ybytes;
-                    if (p.out_dtype == SPX_F32) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4 *>(dst + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else if (p.out_dtype == SPX_F16) {
-                        uint32_t h[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                            h[j] = *reinterpret_cast<uint32_t *>(&t);
-                        }
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-                    } else if (p.out_dtype == SPX_BF16) {
-                        uint32_t h[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            h[j] = *reinterpret_cast<uint32_t *>(&t);
-                        }
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-                    } else {   // SPX_I8: clip(rint(.)) -- numpy round-half-even
-                        uint32_t q[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                float r = fminf(fmaxf(rintf(f[4 * j + b]), -128.f), 127.f);
-                                w |= ((uint32_t)(uint8_t)(int8_t)(int)r) << (8 * b);
-                            }
-                            q[j] = w;
-                        }
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
-                    }
-                }
+            if constexpr (KIND == KIND_F16) {
+                if (p.out_dtype == SPX_F16) epilogue_tile<SPX_F16, false>(p, t_row, dst_row);
+                else epilogue_tile<SPX_BF16, false>(p, t_row, dst_row);
+            } else if constexpr (KIND == KIND_TF32) {
+                epilogue_tile<SPX_F32, false>(p, t_row, dst_row);
+            } else {
+                if (p.out_dtype == SPX_I8) epilogue_tile<SPX_I8, true>(p, t_row, dst_row);
+                else if (p.out_dtype == SPX_F32) epilogue_tile<SPX_F32, true>(p, t_row, dst_row);
+                else epilogue_tile<SPX_F16, true>(p, t_row, dst_row);
             }
             tc_fence_before();
             __syncwarp();
@@ -379,9 +454,10 @@ int make_weight_tmap(CUtensorMap *tm, const void *w, int dtype, int kv, int c_in
     return 0;
 }
 
-static bool span_ok(int bytes) { return bytes == 32 || bytes == 64 || (bytes >= 128 && bytes % 128 == 0); }
+// row bytes the kernels tile: one swizzle span (32/64/128 B) or a power-of-two multiple of 128 B
+static bool span_ok(int bytes) { return bytes == 32 || bytes == 64 || bytes == 128 || bytes == 256 || bytes == 512; }
 
-static bool tc_shape_ok(int dtype, int c_in, int c_out, int transpose_w) {
+static bool tc_shape_ok(int dtype, int kv, int c_in, int c_out, int transpose_w) {
     const int e = dtype_bytes(dtype);
     if (e == 0) return false;
     if (c_in > 256 || c_out > 256) return false;
@@ -392,20 +468,23 @@ static bool tc_shape_ok(int dtype, int c_in, int c_out, int transpose_w) {
     const int xb = (transpose_w ? c_out : c_in) * e;
     if (dtype == SPX_I8 && (c_in % 32 || c_out % 32)) return false;   // docs/INT8_GUIDE.md:10
     size_t stage = align_up((size_t)TC_TILE_M * xb, 1024) + align_up((size_t)c_in * c_out * e, 1024);
-    if (TC_SMEM_BUDGET / stage < 2) return false;
+    const size_t idx = align_up((size_t)(kv + 1) * 512, 1024);
+    if (2 * idx + 2 * stage > (size_t)TC_SMEM_BUDGET) return false;
     return true;
 }
 
 bool tc_gather_gemm_supported(const GatherGemmArgs &a) {
     if (a.dtype == SPX_I8) return false;
+    if (!a.tile_table || !a.tile_mask) return false;   // built by spx_build_tile_table
     // tf32 MN-major operands need the SWIZZLE_128B_BASE32B atom (not tiled here yet): fp32 dgrad -> SIMT
     if (a.dtype == SPX_F32 && a.transpose_w) return false;
     if (((size_t)a.kv * a.c_in * dtype_bytes(a.dtype)) % 16) return false;
-    return tc_shape_ok(a.dtype, a.c_in, a.c_out, a.transpose_w);
+    return tc_shape_ok(a.dtype, a.kv, a.c_in, a.c_out, a.transpose_w);
 }
 bool tc_gather_gemm_int8_supported(const Int8Args &q) {
+    if (!q.g.tile_table || !q.g.tile_mask) return false;
     if (((size_t)q.g.kv * q.g.c_in) % 16) return false;
-    return tc_shape_ok(SPX_I8, q.g.c_in, q.g.c_out, 0);
+    return tc_shape_ok(SPX_I8, q.g.kv, q.g.c_in, q.g.c_out, 0);
 }
 
 static int fill_params(const GatherGemmArgs &a, TcParams &p) {
@@ -415,15 +494,17 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.x = (const uint8_t *)a.x;
     p.xb = cx * e;
     p.span_a = p.xb < 128 ? p.xb : 128;
-    p.ksteps = p.xb / 32;
+    p.lg_span_a = p.span_a == 128 ? 7 : (p.span_a == 64 ? 6 : 5);
+    p.a_subtiles = p.xb / p.span_a;
+    p.q_a = p.span_a / 32;
     const int wb = a.c_in * e;                 // inner (contiguous) bytes of one weight slice row
     p.span_b = wb < 128 ? wb : 128;
     p.b_subtiles = wb / p.span_b;
-    p.b_rows = a.c_out;
     p.b_sub_bytes = a.c_out * p.span_b;
     p.b_bytes = a.c_out * wb;
     p.b_mn_major = a.transpose_w;
-    p.umma_k_rows = 32 / e;
+    p.q_b = p.span_b / 32;
+    p.b_kstep16_mn = ((32 / e) * p.span_b) >> 4;   // one k-step = UMMA_K rows of the weight box
     p.w_inner_elems = a.c_in;
     p.span_b_elems = p.span_b / e;
     p.n = cy;
@@ -432,38 +513,59 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.idesc = make_idesc(c_fmt, ab_fmt, ab_fmt, 0, a.transpose_w, TC_TILE_M, cy);
     p.a_stage_bytes = (int)align_up((size_t)TC_TILE_M * p.xb, 1024);
     p.stage_bytes = p.a_stage_bytes + (int)align_up((size_t)p.b_bytes, 1024);
-    p.stages = TC_SMEM_BUDGET / p.stage_bytes;
+    p.idx_bytes = (int)align_up((size_t)(a.kv + 1) * 512, 1024);
+    p.stages = (TC_SMEM_BUDGET - 2 * p.idx_bytes) / p.stage_bytes;
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
     SPX_REQUIRE(p.stages >= 2, "tc_gather_gemm: tile does not fit shared memory (stage %d bytes)", p.stage_bytes);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * cy)) cols <<= 1;
     p.tmem_cols = cols;
-    p.rows = a.rows; p.pair = a.pair; p.pair_stride = a.pair_stride; p.mask = a.mask; p.argsort = a.argsort;
+    p.rows = a.rows; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask; p.argsort = a.argsort;
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
-    p.mask_out = a.mask_out;
+    return 0;
+}
+
+template <int KIND, int CPR>
+static int launch_tc_cpr(const CUtensorMap &tm, const TcParams &p, cudaStream_t stream) {
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static thread_local bool configured = false;
+    if (!configured) {
+        SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(TC_SMEM_BUDGET + 2048)));
+        configured = true;
+    }
+    const int64_t tiles = div_up64(p.rows, TC_TILE_M);
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    tc_gather_gemm_kernel<KIND, CPR><<<grid, TC_THREADS, smem, stream>>>(tm, p);
+    SPX_CHECK_LAUNCH("tc_gather_gemm_kernel");
     return 0;
 }
 
 template <int KIND>
 static int launch_tc(const CUtensorMap &tm, const TcParams &p, cudaStream_t stream) {
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static thread_local size_t configured[3] = {0, 0, 0};
-    if (configured[KIND] < smem) {
-        SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(TC_SMEM_BUDGET + 2048)));
-        configured[KIND] = TC_SMEM_BUDGET + 2048;
+    switch (p.xb >> 4) {
+        case 2: return launch_tc_cpr<KIND, 2>(tm, p, stream);
+        case 4: return launch_tc_cpr<KIND, 4>(tm, p, stream);
+        case 8: return launch_tc_cpr<KIND, 8>(tm, p, stream);
+        case 16: return launch_tc_cpr<KIND, 16>(tm, p, stream);
+        case 32: return launch_tc_cpr<KIND, 32>(tm, p, stream);
     }
-    const int64_t tiles = div_up64(p.rows, TC_TILE_M);
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    tc_gather_gemm_kernel<KIND><<<grid, TC_THREADS, smem, stream>>>(tm, p);
-    SPX_CHECK_LAUNCH("tc_gather_gemm_kernel");
+    set_error("tc_gather_gemm: unsupported row bytes %d", p.xb);
+    return 2;
+}
+
+static int copy_mask_out(const GatherGemmArgs &a, cudaStream_t stream) {
+    if (!a.mask_out) return 0;      // mask_output_fwd == the per-tile OR masks of the tile table
+    const size_t bytes = (size_t)div_up64(a.rows, TC_TILE_M) * ((a.kv + 31) / 32) * sizeof(uint32_t);
+    SPX_CHECK_CUDA(cudaMemcpyAsync(a.mask_out, a.tile_mask, bytes, cudaMemcpyDeviceToDevice, stream));
     return 0;
 }
 
 int tc_gather_gemm(const GatherGemmArgs &a, cudaStream_t stream) {
     TcParams p;
     if (fill_params(a, p)) return 2;
+    if (copy_mask_out(a, stream)) return 1;
     CUtensorMap tm;
     if (make_weight_tmap(&tm, a.w, a.dtype, a.kv, a.c_in, a.c_out, p.span_b)) return 2;
     if (a.dtype == SPX_F32) return launch_tc<KIND_TF32>(tm, p, stream);
@@ -473,6 +575,7 @@ int tc_gather_gemm(const GatherGemmArgs &a, cudaStream_t stream) {
 int tc_gather_gemm_int8(const Int8Args &q, cudaStream_t stream) {
     TcParams p;
     if (fill_params(q.g, p)) return 2;
+    if (copy_mask_out(q.g, stream)) return 1;
     p.out_dtype = q.out_dtype;
     p.epi_mode = 1;
     p.scale = q.scale; p.bias_f32 = q.bias_f32; p.output_add = q.output_add;

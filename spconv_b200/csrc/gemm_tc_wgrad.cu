@@ -22,19 +22,17 @@ constexpr int WG_MAX_STAGES = 6;
 constexpr int WG_SMEM_BUDGET = 200 * 1024;
 
 struct WgParams {
-    const uint8_t *x; int xb, span_x, apo, apg, atom_elems;
-    const uint8_t *d; int db, span_d;
+    const uint8_t *x; int xb, span_x, lg_span_x, apo, apg, atom_elems;
+    const uint8_t *d; int db, span_d, lg_span_d, lg_cpr_d;
     int n; uint32_t idesc; int ksteps, rows_per_kstep;
     int groups_total, groups_per_pass;
-    int stages, a_stage_bytes, b_buf_bytes;
+    int stages, a_stage_bytes, b_buf_bytes, idx_bytes;
     int64_t rows;
-    const int32_t *pair; int64_t pair_stride;
-    const uint32_t *mask; const int32_t *argsort;
+    const int32_t *tile_table;   // [tiles][kv+1][128]
+    const uint32_t *tile_mask;   // [tiles][words]
     int kv, words, c_in;
     float *partial; int64_t partial_stride;
 };
-
-struct BitIter4 { uint32_t m[4]; };
 
 __device__ __forceinline__ bool bit_set(const uint32_t (&m)[4], int k) { return (m[k >> 5] >> (k & 31)) & 1u; }
 
@@ -47,45 +45,37 @@ __device__ __forceinline__ bool group_active(const uint32_t (&tm)[4], int g, con
     return false;
 }
 
-__device__ __forceinline__ void wg_tile_mask(const uint32_t *__restrict__ mask, int64_t base, int64_t rows, int words,
-                                             int kv, int lane, uint32_t (&out)[4]) {
+__device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ tile_mask, int64_t tile, int words,
+                                                  uint32_t (&out)[4]) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        uint32_t m = 0;
-        if (w < words) {
-            if (mask) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    int64_t row = base + r * 32 + lane;
-                    if (row < rows) m |= __ldg(mask + row * words + w);
-                }
-                m = __reduce_or_sync(0xffffffffu, m);
-            } else {
-                int hi = kv - 32 * w;
-                m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
-            }
-        }
-        out[w] = m;
-    }
+    for (int w = 0; w < 4; ++w) out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
 }
 
+template <int CPA>     // 16-byte chunks per atom row (= span_x / 16)
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgParams p) {
+    constexpr int LG_CPA = CPA == 2 ? 1 : (CPA == 4 ? 2 : 3);
+    constexpr int RPI = 32 / CPA;
+    constexpr int SPAN_X = CPA * 16;
+    constexpr int LG_SPAN_X = LG_CPA + 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t *smem = smem_raw + pad;
     const uint32_t smem_base = raw_addr + pad;
-    // layout: [2 x B buffer][stages x A stage][barriers]
+    // layout: [2 x B buffer][stages x A stage][2 x index block][barriers]
     const uint32_t b_base = smem_base;
     const uint32_t a_base = smem_base + 2u * p.b_buf_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes);
+    const uint32_t idx_off = 2u * p.b_buf_bytes + (uint32_t)p.stages * p.a_stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + idx_off + 2u * p.idx_bytes);
     uint64_t *full_a = bars;                          // [stages]
     uint64_t *empty_a = bars + WG_MAX_STAGES;         // [stages]
     uint64_t *full_b = bars + 2 * WG_MAX_STAGES;      // [2]
     uint64_t *empty_b = bars + 2 * WG_MAX_STAGES + 2; // [2]
-    uint64_t *acc_done = bars + 2 * WG_MAX_STAGES + 4;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * WG_MAX_STAGES + 5);
+    uint64_t *idx_full = bars + 2 * WG_MAX_STAGES + 4;  // [2]
+    uint64_t *idx_empty = bars + 2 * WG_MAX_STAGES + 6; // [2]
+    uint64_t *acc_done = bars + 2 * WG_MAX_STAGES + 8;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * WG_MAX_STAGES + 9);
     uint32_t *used_smem = tmem_ptr_smem + 1;
 
     const int warp = threadIdx.x >> 5;
@@ -97,7 +87,10 @@ tc_wgrad_kernel(const WgParams p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&full_b[b], 128); mbar_init(&empty_b[b], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full_b[b], 128); mbar_init(&empty_b[b], 1);
+            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], 128);
+        }
         mbar_init(acc_done, 1);
         *used_smem = 0;
         mbar_fence_init();
@@ -115,110 +108,147 @@ tc_wgrad_kernel(const WgParams p) {
     if (warp >= 4 && warp < 8) {
         // ================================================= producers
         const int pw = warp - 4;
+        const bool leader = (pw == 0 && lane == 0);
+        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;                                  // B buffers filled so far
         const int cpr_d = p.db >> 4;                      // 16-byte chunks per dout row
-        const int cpa = p.span_x >> 4;                    // chunks per atom row
-        for (int64_t tile = chunk; tile < num_tiles; tile += chunks) {
-            const int64_t base = tile * WG_TILE;
-            uint32_t tm[4];
-            wg_tile_mask(p.mask, base, p.rows, p.words, p.kv, lane, tm);
+        // per-lane constants of the atom gather: chunk chb of rows r0 + itc*RPI of this warp's 32 rows
+        const int r0 = lane >> LG_CPA;
+        const uint32_t chb = (uint32_t)(lane & (CPA - 1)) << 4;
+        const uint8_t *x_lane = p.x + chb;
+        uint32_t dst_off[CPA];
+#pragma unroll
+        for (int itc = 0; itc < CPA; ++itc)
+            dst_off[itc] = swizzle_offset(((uint32_t)(pw * 32 + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
+        const int lg_apo = p.apo == 1 ? 0 : (p.apo == 2 ? 1 : 2);
+        auto fetch_indices = [&](int64_t t, int64_t lcl) {
+            const int b = (int)(lcl & 1);
+            const uint32_t use = (uint32_t)(lcl >> 1);
+            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
+            bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
+                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
+        };
+        int64_t local = 0;
+        int64_t tile = chunk;
+        uint32_t tm[4] = {0, 0, 0, 0};
+        if (tile < num_tiles) {
+            if (leader) fetch_indices(tile, 0);
+            wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
+        }
+        for (; tile < num_tiles; tile += chunks, ++local) {
+            const int buf = (int)(local & 1);
+            const int64_t next = tile + chunks;
+            uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (next < num_tiles) {
+                wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
+                if (leader) fetch_indices(next, local + 1);
+            }
+            mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
             bool any = false;
             for (int g = g_begin; g < g_end; ++g) any = any || group_active(tm, g, p);
-            if (!any) continue;
-            const int64_t my_row = base + pw * 32 + lane;
-            int32_t src_row = -1;
-            if (my_row < p.rows) src_row = p.argsort ? __ldg(p.argsort + my_row) : (int32_t)my_row;
-            // ---- dout tile (MN-major B operand)
-            {
-                const int bb = (int)(nb & 1);
-                mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
-                const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
-                for (int itc = 0; itc < cpr_d; ++itc) {
-                    const int flat = itc * 32 + lane;
-                    const int r = flat / cpr_d;
-                    const int ch = flat - r * cpr_d;
-                    const int32_t rsrc = __shfl_sync(0xffffffffu, src_row, r);
-                    const uint32_t byte_in_row = (uint32_t)ch << 4;
-                    const uint32_t sub = byte_in_row / (uint32_t)p.span_d;
-                    const uint32_t within = byte_in_row - sub * p.span_d;
-                    const uint32_t row_in_tile = (uint32_t)(pw * 32 + r);
-                    const uint32_t dst = dstb + sub * (uint32_t)(WG_TILE * p.span_d) +
-                                         swizzle_offset(row_in_tile * p.span_d + within, p.span_d);
-                    const uint8_t *src = p.d + (rsrc >= 0 ? (int64_t)rsrc * p.db + byte_in_row : 0);
-                    cp_async_16(dst, src, rsrc >= 0 ? 16u : 0u);
-                }
-                cp_async_mbar_arrive_noinc(&full_b[bb]);
-                ++nb;
-            }
-            // ---- gathered x atoms, one stage per active group
-            for (int g = g_begin; g < g_end; ++g) {
-                if (!group_active(tm, g, p)) continue;
-                mbar_wait(&empty_a[stage], phase ^ 1u);
-                const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
-                for (int s = 0; s < p.apg; ++s) {
-                    const int a = g * p.apg + s;
-                    const int k = a / p.apo;
-                    const int cb = a - k * p.apo;
-                    int32_t idx = -1;
-                    if (k < p.kv && bit_set(tm, k) && src_row >= 0)
-                        idx = __ldg(p.pair + (int64_t)k * p.pair_stride + src_row);
-                    const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * p.span_x);
-                    for (int itc = 0; itc < cpa; ++itc) {
+            if (any) {
+                const int32_t *idx_s = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes);
+                // ---- dout tile (MN-major B operand); source rows are block row kv
+                {
+                    const int bb = (int)(nb & 1);
+                    mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
+                    const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
+                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * 32;
+                    for (int itc = 0; itc < cpr_d; ++itc) {
                         const int flat = itc * 32 + lane;
-                        const int r = flat / cpa;
-                        const int ch = flat - r * cpa;
-                        const int32_t ridx = __shfl_sync(0xffffffffu, idx, r);
+                        const int r = flat >> p.lg_cpr_d;
+                        const uint32_t byte_in_row = (uint32_t)(flat & (cpr_d - 1)) << 4;
+                        const int32_t rsrc = rows_s[r];
+                        const uint32_t sub = byte_in_row >> p.lg_span_d;
+                        const uint32_t within = byte_in_row & (uint32_t)(p.span_d - 1);
                         const uint32_t row_in_tile = (uint32_t)(pw * 32 + r);
-                        const uint32_t dst = atom_base + swizzle_offset(row_in_tile * p.span_x + ((uint32_t)ch << 4), p.span_x);
-                        const uint8_t *src = p.x + (ridx >= 0 ? (int64_t)ridx * p.xb + (int64_t)cb * p.span_x + (ch << 4) : 0);
-                        cp_async_16(dst, src, ridx >= 0 ? 16u : 0u);
+                        const uint32_t dst = dstb + sub * (uint32_t)(WG_TILE * p.span_d) +
+                                             swizzle_offset((row_in_tile << p.lg_span_d) + within, p.span_d);
+                        const uint8_t *src = p.d + (rsrc >= 0 ? (int64_t)rsrc * p.db + byte_in_row : 0);
+                        cp_async_16(dst, src, rsrc >= 0 ? 16u : 0u);
                     }
+                    cp_async_mbar_arrive_noinc(&full_b[bb]);
+                    ++nb;
                 }
-                cp_async_mbar_arrive_noinc(&full_a[stage]);
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                // ---- gathered x atoms, one stage per active group
+                for (int g = g_begin; g < g_end; ++g) {
+                    if (!group_active(tm, g, p)) continue;
+                    mbar_wait(&empty_a[stage], phase ^ 1u);
+                    const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
+                    for (int s = 0; s < p.apg; ++s) {
+                        const int a = g * p.apg + s;
+                        const int k = a >> lg_apo;
+                        const int cb = a & (p.apo - 1);
+                        const bool active = k < p.kv && bit_set(tm, k);
+                        const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * 32 + r0;
+                        const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * SPAN_X);
+                        const uint8_t *x_atom = x_lane + cb * SPAN_X;
+#pragma unroll
+                        for (int itc = 0; itc < CPA; ++itc) {
+                            const int32_t ridx = active ? idx_k[itc * RPI] : -1;
+                            cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx, 0) * p.xb,
+                                        ridx >= 0 ? 16u : 0u);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&full_a[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
             }
+            mbar_arrive(&idx_empty[buf]);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
     } else if (warp == 8) {
         // ================================================= MMA issuer
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;
         uint32_t used = 0;
-        for (int64_t tile = chunk; tile < num_tiles; tile += chunks) {
-            const int64_t base = tile * WG_TILE;
-            uint32_t tm[4];
-            wg_tile_mask(p.mask, base, p.rows, p.words, p.kv, lane, tm);
+        int64_t tile = chunk;
+        uint32_t tm[4] = {0, 0, 0, 0};
+        if (tile < num_tiles) wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
+        // both operands are MN-major: LBO = distance between 128-row atoms, SBO = 8 rows
+        const uint64_t a_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
+        const uint64_t b_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_d), 8u * p.span_d, p.span_d);
+        const uint32_t a_step16 = (uint32_t)(p.rows_per_kstep * p.span_x) >> 4;
+        const uint32_t b_step16 = (uint32_t)(p.rows_per_kstep * p.span_d) >> 4;
+        for (; tile < num_tiles; tile += chunks) {
+            const int64_t next = tile + chunks;
+            uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (next < num_tiles) wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
             bool any = false;
             for (int g = g_begin; g < g_end; ++g) any = any || group_active(tm, g, p);
-            if (!any) continue;
-            const int bb = (int)(nb & 1);
-            mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
-            const uint32_t b_buf = b_base + (uint32_t)bb * p.b_buf_bytes;
-            for (int g = g_begin; g < g_end; ++g) {
-                if (!group_active(tm, g, p)) continue;
-                mbar_wait(&full_a[stage], phase);
-                tc_fence_after();
-                fence_proxy_async_smem();
-                const int gl = g - g_begin;
-                if (lane == 0) {
-                    const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(gl * p.n);
-                    for (int j = 0; j < p.ksteps; ++j) {
-                        const uint64_t a_desc = make_smem_desc(a_stage + (uint32_t)j * p.rows_per_kstep * p.span_x,
-                                                               (uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
-                        const uint64_t b_desc = make_smem_desc(b_buf + (uint32_t)j * p.rows_per_kstep * p.span_d,
-                                                               (uint32_t)(WG_TILE * p.span_d), 8u * p.span_d, p.span_d);
-                        umma_ss<KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, (((used >> gl) & 1u) || j > 0) ? 1u : 0u);
+            if (any) {
+                const int bb = (int)(nb & 1);
+                mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
+                const uint32_t b16 = (b_base + (uint32_t)bb * p.b_buf_bytes) >> 4;
+                for (int g = g_begin; g < g_end; ++g) {
+                    if (!group_active(tm, g, p)) continue;
+                    mbar_wait(&full_a[stage], phase);
+                    tc_fence_after();
+                    fence_proxy_async_smem();
+                    const int gl = g - g_begin;
+                    if (lane == 0) {
+                        const uint32_t a16 = (a_base + (uint32_t)stage * p.a_stage_bytes) >> 4;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(gl * p.n);
+                        for (int j = 0; j < p.ksteps; ++j) {
+                            const uint64_t a_desc = a_hi | (uint64_t)((a16 + (uint32_t)j * a_step16) & 0x3FFFu);
+                            const uint64_t b_desc = b_hi | (uint64_t)((b16 + (uint32_t)j * b_step16) & 0x3FFFu);
+                            umma_ss<KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, (((used >> gl) & 1u) || j > 0) ? 1u : 0u);
+                        }
+                        tc_commit(&empty_a[stage]);
                     }
-                    tc_commit(&empty_a[stage]);
+                    __syncwarp();
+                    used |= 1u << gl;
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                if (lane == 0) tc_commit(&empty_b[bb]);
                 __syncwarp();
-                used |= 1u << gl;
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                ++nb;
             }
-            if (lane == 0) tc_commit(&empty_b[bb]);
-            __syncwarp();
-            ++nb;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
         if (lane == 0) {
             *used_smem = used;
@@ -285,16 +315,22 @@ struct WgPlan { WgParams p; int passes, chunks; size_t smem; };
 
 static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     if (a.dtype != SPX_F16 && a.dtype != SPX_BF16) return false;     // tf32 MN-major needs SW128_32B atoms
+    if (!a.tile_table || !a.tile_mask) return false;                 // built by spx_build_tile_table
     const int e = 2;
     if (a.c_in % 16 || a.c_out % 16 || a.c_in > 256 || a.c_out > 256) return false;
     if (!wg_span_ok(a.c_in * e) || !wg_span_ok(a.c_out * e)) return false;
     WgParams &p = pl.p;
     memset(&p, 0, sizeof(p));
     p.xb = a.c_in * e; p.span_x = p.xb < 128 ? p.xb : 128;
+    p.lg_span_x = p.span_x == 128 ? 7 : (p.span_x == 64 ? 6 : 5);
     p.apo = p.xb / p.span_x;
     p.atom_elems = p.span_x / e;
     p.apg = 128 / p.atom_elems;
     p.db = a.c_out * e; p.span_d = p.db < 128 ? p.db : 128;
+    p.lg_span_d = p.span_d == 128 ? 7 : (p.span_d == 64 ? 6 : 5);
+    if (p.db & (p.db - 1)) return false;
+    p.lg_cpr_d = 0;
+    while ((1 << p.lg_cpr_d) < (p.db >> 4)) ++p.lg_cpr_d;
     p.n = a.c_out;
     p.rows_per_kstep = 32 / e;
     p.ksteps = WG_TILE / p.rows_per_kstep;
@@ -307,18 +343,19 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     pl.passes = (p.groups_total + p.groups_per_pass - 1) / p.groups_per_pass;
     p.a_stage_bytes = p.apg * WG_TILE * p.span_x;
     p.b_buf_bytes = WG_TILE * p.db;
-    int avail = WG_SMEM_BUDGET - 2 * p.b_buf_bytes;
+    p.idx_bytes = (int)align_up((size_t)(a.kv + 1) * 512, 1024);
+    int avail = WG_SMEM_BUDGET - 2 * p.b_buf_bytes - 2 * p.idx_bytes;
     if (avail < 2 * p.a_stage_bytes) return false;
     p.stages = avail / p.a_stage_bytes;
     if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
-    pl.smem = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 1024 + 256;
+    pl.smem = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 2 * (size_t)p.idx_bytes + 1024 + 256;
     int64_t tiles = div_up64(a.n_out, WG_TILE);
     int chunks = sm_count() / pl.passes;
     if (chunks < 1) chunks = 1;
     if (chunks > tiles) chunks = (int)tiles;
     if (chunks < 1) chunks = 1;
     pl.chunks = chunks;
-    p.rows = a.n_out; p.pair = a.pair; p.pair_stride = a.pair_stride; p.mask = a.mask; p.argsort = a.argsort;
+    p.rows = a.n_out; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask;
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.c_in = a.c_in;
     p.x = (const uint8_t *)a.x; p.d = (const uint8_t *)a.dout;
     p.partial_stride = (int64_t)a.kv * a.c_in * a.c_out;
@@ -343,14 +380,19 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     pl.p.partial = (float *)a.workspace;
     SPX_REQUIRE((size_t)pl.chunks * pl.p.partial_stride * sizeof(float) <= a.workspace_bytes,
                 "tc_wgrad: workspace too small");
-    static thread_local bool configured = false;
-    if (!configured) {
-        SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            WG_SMEM_BUDGET + 2048));
-        configured = true;
-    }
     dim3 grid(pl.chunks, pl.passes);
-    tc_wgrad_kernel<<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
+    static thread_local bool configured[3] = {false, false, false};
+    const int cpa = pl.p.span_x >> 4;
+    const int ci = cpa == 2 ? 0 : (cpa == 4 ? 1 : 2);
+    if (!configured[ci]) {
+        const void *fn = cpa == 2 ? (const void *)tc_wgrad_kernel<2> : cpa == 4 ? (const void *)tc_wgrad_kernel<4>
+                                                                               : (const void *)tc_wgrad_kernel<8>;
+        SPX_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BUDGET + 2048));
+        configured[ci] = true;
+    }
+    if (cpa == 2) tc_wgrad_kernel<2><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
+    else if (cpa == 4) tc_wgrad_kernel<4><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
+    else tc_wgrad_kernel<8><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
     SPX_CHECK_LAUNCH("tc_wgrad_kernel");
     const int64_t total = pl.p.partial_stride;
     unsigned nblk = (unsigned)div_up64(total, 256);

@@ -233,6 +233,68 @@ __global__ void subm_probe_kernel(Table table, Geom g, const int32_t *__restrict
     }
 }
 
+// 3-D, 3x3x3 (any dilation), 32-bit keys -- the shape of every SubMConv3d in SECOND-style nets.
+// The neighbour key is the centre key plus a per-offset constant, validity is a product of three
+// per-axis range tests, and the nine probes of one z-plane are issued back to back so a thread
+// keeps nine independent 8-byte loads in flight (the generic kernel above exposes one L2 round
+// trip per offset and spends ~150 instructions per probe on generic n-d index arithmetic).
+__global__ void __launch_bounds__(128)
+subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices, int64_t N,
+                     int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
+                     uint32_t *__restrict__ mask) {
+    const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + o);    // (b, z, y, x)
+    const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
+    const int dz = g.dilation[0], dy = g.dilation[1], dx = g.dilation[2];
+    const bool bok = c.x >= 0 && c.x < g.batch;
+    // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
+    bool vz[3], vy[3], vx[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int qz = c.y + (r - 1) * dz, qy = c.z + (r - 1) * dy, qx = c.w + (r - 1) * dx;
+        vz[r] = bok && qz >= 0 && qz < D0;
+        vy[r] = qy >= 0 && qy < D1;
+        vx[r] = qx >= 0 && qx < D2;
+    }
+    const uint32_t key_c = (uint32_t)(((c.x * D0 + c.y) * D1 + c.z) * D2 + c.w);
+    const int sz = dz * D1 * D2, sy = dy * D2, sx = dx;
+    uint32_t mword = 0;
+#pragma unroll
+    for (int rz = 0; rz < 3; ++rz) {
+        unsigned long long slot[9];
+        uint32_t key[9], hpos[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int ry = j / 3, rx = j % 3;
+            const bool valid = vz[rz] && vy[ry] && vx[rx] && !(rz == 1 && j == 4);
+            key[j] = key_c + (uint32_t)((rz - 1) * sz + (ry - 1) * sy + (rx - 1) * sx);
+            hpos[j] = mix32(key[j]) & table.cap_mask;
+            slot[j] = valid ? __ldg(&table.slots[hpos[j]]) : Table32::EMPTY;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int k = rz * 9 + j;
+            int32_t found = -1;
+            if (k == 13) {
+                found = (int32_t)o;                       // centre: identity
+            } else {
+                unsigned long long cur = slot[j];
+                uint32_t h = hpos[j];
+                while (cur != Table32::EMPTY) {           // collision chain (rare at load factor <= 0.5)
+                    if ((uint32_t)(cur >> 32) == key[j]) { found = (int32_t)(uint32_t)cur; break; }
+                    h = (h + 1) & table.cap_mask;
+                    cur = __ldg(&table.slots[h]);
+                }
+            }
+            pair_fwd[(int64_t)k * N + o] = found;
+            if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
+            if (found >= 0) mword |= 1u << k;
+        }
+    }
+    if (mask) mask[o] = mword;
+}
+
 // ------------------------------------------------------------------ regular / transposed conv
 __device__ __forceinline__ bool conv_out_coord(const Geom &g, const int (&c)[SPX_MAX_NDIM + 1],
                                                const int (&r)[SPX_MAX_NDIM], int (&o)[SPX_MAX_NDIM + 1]) {
@@ -467,6 +529,35 @@ __global__ void gather_rows_kernel(const uint32_t *__restrict__ src, const int32
     for (int w = 0; w < words; ++w) dst[i * words + w] = src[(int64_t)perm[i] * words + w];
 }
 
+// ------------------------------------------------------------------ tile-blocked gather table
+// one block per 128-row tile; see include/spconv_b200.h (spx_build_tile_table)
+__global__ void __launch_bounds__(128)
+build_tile_table_kernel(const int32_t *__restrict__ pair, int64_t pair_stride, int kv,
+                        const int32_t *__restrict__ argsort, const uint32_t *__restrict__ mask, int64_t rows,
+                        int words, int32_t *__restrict__ table, uint32_t *__restrict__ tile_mask) {
+    const int64_t t = blockIdx.x;
+    const int r = threadIdx.x;
+    const int64_t j = t * 128 + r;
+    int32_t src = -1;
+    if (j < rows) src = argsort ? __ldg(argsort + j) : (int32_t)j;
+    int32_t *blk = table + t * (int64_t)(kv + 1) * 128;
+    for (int k = 0; k < kv; ++k)
+        blk[k * 128 + r] = src >= 0 ? __ldg(pair + (int64_t)k * pair_stride + src) : -1;
+    blk[kv * 128 + r] = src;
+    __shared__ uint32_t red[4][4];
+    for (int w = 0; w < words; ++w) {
+        uint32_t m = 0;
+        if (j < rows) {
+            if (mask) m = __ldg(mask + j * words + w);
+            else { int hi = kv - 32 * w; m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u); }
+        }
+        m = __reduce_or_sync(0xffffffffu, m);
+        if ((r & 31) == 0) red[w][r >> 5] = m;
+    }
+    __syncthreads();
+    if (r < words) tile_mask[t * words + r] = red[r][0] | red[r][1] | red[r][2] | red[r][3];
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -559,7 +650,11 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
         Table32 t{(unsigned long long *)tbl, L.capacity - 1};
         subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("subm_insert_kernel");
-        subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
+        if (gg.ndim == 3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3) {
+            subm_probe_k3_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask);
+        } else {
+            subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
+        }
         SPX_CHECK_LAUNCH("subm_probe_kernel");
     } else {
         SPX_CHECK_CUDA(cudaMemsetAsync(tvals, 0x7F, (size_t)L.capacity * 4, stream));
@@ -793,5 +888,23 @@ extern "C" int spx_mask_argsort(uint32_t *mask, int32_t *argsort, int64_t N, int
     gather_rows_kernel<<<nblk, 256, 0, stream>>>(mask, argsort, N, words, rows_tmp);
     SPX_CHECK_LAUNCH("gather_rows_kernel");
     SPX_CHECK_CUDA(cudaMemcpyAsync(mask, rows_tmp, (size_t)N * words * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+extern "C" size_t spx_tile_table_elems(int64_t rows, int kv) {
+    return (size_t)div_up64(rows > 0 ? rows : 1, 128) * (size_t)(kv + 1) * 128;
+}
+
+extern "C" int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, int kv, const int32_t *argsort,
+                                    const uint32_t *mask, int64_t rows, int32_t *table, uint32_t *tile_mask,
+                                    spx_stream_t stream_) {
+    SPX_REQUIRE(kv >= 1 && kv <= 128, "build_tile_table: kernel volume %d not in [1,128]", kv);
+    if (rows == 0) return 0;
+    SPX_REQUIRE(pair && table && tile_mask, "build_tile_table: NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int words = (kv + 31) / 32;
+    build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128, 0, stream>>>(pair, pair_stride, kv, argsort, mask,
+                                                                             rows, words, table, tile_mask);
+    SPX_CHECK_LAUNCH("build_tile_table_kernel");
     return 0;
 }

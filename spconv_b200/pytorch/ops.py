@@ -266,7 +266,32 @@ def _f32_mode() -> int:
     return _cabi.SPX_F32_TF32 if SPCONV_ALLOW_TF32 else _cabi.SPX_F32_EXACT
 
 
-def _desc(dtype, kv, c_in, c_out, n_in, n_out, pair, mask, argsort, reverse=False):
+def _tile_tables(pair: torch.Tensor, mask: Optional[torch.Tensor], argsort: Optional[torch.Tensor],
+                 rows: int, kv: int, owner: Optional[torch.Tensor] = None):
+    """Tile-blocked gather table + per-tile OR masks for (pair, mask, argsort)
+    (``spx_build_tile_table``).  Built once per rulebook and cached on ``owner`` (the argsort
+    tensor that lives in the cached ``ImplicitGemmIndiceData``), so forward, input-gradient and
+    weight-gradient of every layer sharing the ``indice_key`` reuse it."""
+    key = (pair.data_ptr(), tuple(pair.shape), pair._version,
+           None if argsort is None else (argsort.data_ptr(), argsort._version), int(rows))
+    if owner is not None:
+        hit = getattr(owner, "_spx_tile_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+    lib = _lib()
+    words = (kv + 31) // 32
+    tiles = max((int(rows) + MASK_WIDTH - 1) // MASK_WIDTH, 1)
+    table = torch.empty((lib.spx_tile_table_elems(int(rows), kv),), dtype=torch.int32, device=pair.device)
+    tile_mask = torch.empty((tiles, words), dtype=torch.int32, device=pair.device)
+    _cabi.check(lib.spx_build_tile_table(_ptr(pair), int(pair.stride(0)), kv, _ptr(argsort), _ptr(mask),
+                                         int(rows), _ptr(table), _ptr(tile_mask), _stream()),
+                "build_tile_table")
+    if owner is not None:
+        owner._spx_tile_cache = (key, table, tile_mask)
+    return table, tile_mask
+
+
+def _desc(dtype, kv, c_in, c_out, n_in, n_out, pair, mask, argsort, reverse=False, tiles=None):
     d = _cabi.GemmDesc()
     d.dtype = _DTYPE_CODE[dtype]
     d.f32_mode = _f32_mode()
@@ -277,6 +302,9 @@ def _desc(dtype, kv, c_in, c_out, n_in, n_out, pair, mask, argsort, reverse=Fals
     d.mask = _ptr(mask)
     d.argsort = _ptr(argsort)
     d.reverse_offsets = int(bool(reverse))
+    if tiles is not None:
+        d.tile_table = _ptr(tiles[0])
+        d.tile_mask = _ptr(tiles[1])
     return d
 
 
@@ -322,18 +350,23 @@ def implicit_gemm(features: torch.Tensor, filters: torch.Tensor, pair_fwd: torch
     if output_dtype is None:
         output_dtype = features.dtype
     words = (kv + 31) // 32
-    mask_output = torch.empty((1, (n_out + MASK_WIDTH - 1) // MASK_WIDTH, words), dtype=torch.int32,
-                              device=features.device) if is_train else torch.Tensor()
-    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask, argsort)
+    with timer.record("tile_table", _stream()):
+        tiles = _tile_tables(pair_fwd, mask, argsort, n_out, kv, owner=argsort) if n_out else None
+    # mask_output_fwd (per-128-row OR of the sorted masks) is the tile table's mask block
+    mask_output = tiles[1].view(1, -1, words) if (is_train and tiles is not None) else torch.Tensor()
+    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask, argsort, tiles=tiles)
     if is_int8:
         assert scale is not None, "int8 implicit gemm needs the per-channel scale"
         out = torch.empty((n_out, c_out), dtype=output_dtype, device=features.device)
-        scale_f = (scale.float() * float(output_scale)).contiguous() if output_scale != 1.0 else scale.float().contiguous()
+        # reference int8 epilogue (convops.py:2176-2206): per-channel `scale` multiplies the int32
+        # accumulator, the residual enters with beta = output_add_scale / output_scale
+        scale_f = scale.float().contiguous()
         bias_f = bias.float().contiguous() if bias is not None else None
         with timer.record("implicit_gemm_int8", _stream()):
             _cabi.check(lib.spx_implicit_gemm_fwd_int8(
                 ctypes.byref(d), _ptr(features), _ptr(filters), _ptr(out), _DTYPE_CODE[output_dtype],
-                _ptr(scale_f), _ptr(bias_f), _ptr(output_add), float(output_add_scale),
+                _ptr(scale_f), _ptr(bias_f), _ptr(output_add),
+                float(output_add_scale) / float(output_scale if output_scale else 1.0),
                 _act_code(act_type), float(act_alpha), _stream()), "implicit_gemm_fwd_int8")
         return out, mask_output, MASK_WIDTH
     out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
@@ -342,8 +375,7 @@ def implicit_gemm(features: torch.Tensor, filters: torch.Tensor, pair_fwd: torch
     with timer.record("implicit_gemm", _stream()):
         _cabi.check(lib.spx_implicit_gemm_fwd(ctypes.byref(d), _ptr(features), _ptr(filters),
                                               _ptr(out), _ptr(bias), _act_code(act_type),
-                                              float(act_alpha), _ptr(mask_output) if is_train else None,
-                                              _stream()), "implicit_gemm_fwd")
+                                              float(act_alpha), None, _stream()), "implicit_gemm_fwd")
     if output_add is not None:
         out = out + output_add
     if output_dtype != out.dtype:
@@ -375,18 +407,22 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
     din = torch.empty_like(features)
     dfilters = torch.empty_like(filters)
     mask_fwd, argsort_fwd = _first(pair_mask_fwd_splits), _first(mask_argsort_fwd_splits)
+    tiles_fwd = _tile_tables(pair_fwd, mask_fwd, argsort_fwd, n_out, kv, owner=argsort_fwd) if n_out else None
     if is_subm:
         # SubM pairs are symmetric: walk the FORWARD table/mask and flip the filter offset
         # (the reference's reverse_mask, convops.py:2412)
         d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask_fwd, argsort_fwd,
-                     reverse=True)
+                     reverse=True, tiles=tiles_fwd)
     else:
-        d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_bwd,
-                     _first(pair_mask_bwd_splits), _first(mask_argsort_bwd_splits))
+        mask_bwd, argsort_bwd = _first(pair_mask_bwd_splits), _first(mask_argsort_bwd_splits)
+        tiles_bwd = _tile_tables(pair_bwd, mask_bwd, argsort_bwd, n_in, kv, owner=argsort_bwd) if n_in else None
+        d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_bwd, mask_bwd, argsort_bwd,
+                     tiles=tiles_bwd)
     with timer.record("implicit_gemm_dgrad", _stream()):
         _cabi.check(lib.spx_implicit_gemm_dgrad(ctypes.byref(d_dg), _ptr(out_bp), _ptr(filters),
                                                 _ptr(din), _stream()), "implicit_gemm_dgrad")
-    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask_fwd, argsort_fwd)
+    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask_fwd, argsort_fwd,
+                 tiles=tiles_fwd)
     ws_bytes = lib.spx_implicit_gemm_wgrad_workspace_size(ctypes.byref(d_wg))
     ws = _bytes(ws_bytes, features.device)
     with timer.record("implicit_gemm_wgrad", _stream()):
@@ -439,7 +475,8 @@ def indice_conv(features: torch.Tensor, filters: torch.Tensor, indice_pairs: tor
     out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
     if bias is not None:
         bias = bias.to(features.dtype).contiguous()
-    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None)
+    tiles = _tile_tables(t_fwd, m_fwd, None, n_out, kv) if n_out else None
+    d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None, tiles=tiles)
     with timer.record("indice_conv", _stream()):
         _cabi.check(lib.spx_implicit_gemm_fwd(ctypes.byref(d), _ptr(features), _ptr(filters),
                                               _ptr(out), _ptr(bias), _act_code(act_type),
@@ -469,11 +506,13 @@ def indice_conv_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: 
                                                 subm, inverse, True, True)
     din = torch.empty_like(features)
     dfilters = torch.empty_like(filters)
-    d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_bwd, m_bwd, None)
+    tiles_bwd = _tile_tables(t_bwd, m_bwd, None, n_in, kv) if n_in else None
+    tiles_fwd = _tile_tables(t_fwd, m_fwd, None, n_out, kv) if n_out else None
+    d_dg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_bwd, m_bwd, None, tiles=tiles_bwd)
     with timer.record("indice_conv_dgrad", _stream()):
         _cabi.check(lib.spx_implicit_gemm_dgrad(ctypes.byref(d_dg), _ptr(out_bp), _ptr(filters),
                                                 _ptr(din), _stream()), "implicit_gemm_dgrad(native)")
-    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None)
+    d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None, tiles=tiles_fwd)
     ws = _bytes(lib.spx_implicit_gemm_wgrad_workspace_size(ctypes.byref(d_wg)), features.device)
     with timer.record("indice_conv_wgrad", _stream()):
         _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),

@@ -204,3 +204,50 @@ def test_empty_and_tiny_inputs(oracle, cuda_dev):
     ref = oracle.indice_conv(x.float().cpu().numpy(), w.float().cpu().numpy(), o_pairs[1],
                              o_pairs[2], 129, False, True)
     assert rel_l2(out.float().cpu().numpy(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("subm", [True, False], ids=["subm", "conv"])
+@pytest.mark.parametrize("CK", [(64, 64), (32, 64), (16, 16)], ids=lambda ck: f"C{ck[0]}K{ck[1]}")
+@pytest.mark.parametrize("out_int8", [True, False], ids=["q8", "f32out"])
+def test_int8_inference_forward(CK, subm, out_int8, oracle, cuda_dev):
+    """int8 x int8 -> int32 accumulate -> per-channel scale + bias (+ residual) -> act ->
+    clip(round()) : exact match with the numpy formula of test/test_all_algo.py:222-287
+    (inputs randint(-1,1)-style small integers, scales U(0.5,1.5), output_add_scale 14.2)."""
+    import os
+    from spconv_b200.core import Activation, ConvAlgo
+    from spconv_b200.pytorch import ops
+    C, K = CK
+    rng = np.random.default_rng(50005)
+    shape = [19, 18, 17]
+    _, inds = random_cloud(rng, shape, [1500, 1500], 1)
+    ks, st, pd, dl = [3] * 3, [1 if subm else 2] * 3, [1] * 3, [1] * 3
+    x = rng.integers(-4, 4, size=(inds.shape[0], C)).astype(np.int8)
+    w = rng.integers(-4, 4, size=(K, 3, 3, 3, C)).astype(np.int8)
+    out_inds, pairs, num = oracle.get_indice_pairs(inds, 2, shape, ks, st, pd, dl, [0] * 3, subm)
+    m = out_inds.shape[0]
+    scales = rng.uniform(0.5, 1.5, size=K).astype(np.float32) * 0.05
+    bias = rng.uniform(-5, 5, size=K).astype(np.float32)
+    add = rng.integers(-2, 2, size=(m, K)).astype(np.int8)
+    output_scale, add_scale = 3.4, 14.2 * 0.1
+    ref = oracle.int8_conv_forward(x, w, pairs, num, m, subm, scales, bias, add,
+                                   np.float32(add_scale) / np.float32(output_scale), relu=True,
+                                   out_int8=out_int8)
+    d_inds = torch.from_numpy(inds).to(cuda_dev)
+    res = ops.get_indice_pairs_implicit_gemm(d_inds, 2, shape, ConvAlgo.MaskImplicitGemm, ks, st, pd, dl,
+                                             [0] * 3, subm, False, is_train=False)
+    assert np.array_equal(res[0].cpu().numpy(), out_inds)
+    out, _, _ = ops.implicit_gemm(torch.from_numpy(x).to(cuda_dev), torch.from_numpy(w).to(cuda_dev), res[2],
+                                  res[4], res[6], m, res[8], False, subm, bias=torch.from_numpy(bias).to(cuda_dev),
+                                  act_type=Activation.ReLU, output_scale=output_scale,
+                                  scale=torch.from_numpy(scales).to(cuda_dev),
+                                  output_add=torch.from_numpy(add).to(cuda_dev), output_add_scale=add_scale,
+                                  output_dtype=torch.int8 if out_int8 else torch.float32)
+    got = out.cpu().numpy()
+    if C % 32 == 0 and K % 32 == 0 and os.environ.get("SPX_FORCE_SIMT") != "1":
+        assert ops.last_kernel_family() == 2, "int8 tcgen05 (kind::i8) path expected"   # docs/INT8_GUIDE.md:10
+    if out_int8:
+        # fp32 evaluation order can differ by 1 ulp exactly at .5 ties: allow off-by-one there only
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (diff.max(), (diff > 0).mean())
+    else:
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())

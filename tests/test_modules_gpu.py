@@ -89,11 +89,11 @@ def test_indice_key_reuse_and_errors(cuda_dev):
     assert y.spatial_shape == shape and y.features.shape == (2500, 16)
     assert torch.isfinite(y.features.float()).all()
     # same key, different kernel size -> reference error text
-    bad = spconv.SubMConv3d(16, 16, 5, indice_key="subm1").to(cuda_dev).half()
+    bad = spconv.SubMConv3d(16, 16, 5, indice_key="subm1", large_kernel_fast_algo=True).to(cuda_dev).half()
     with pytest.raises(ValueError, match="same kernel size"):
         bad(net[0](x))
     # a regular conv cannot reuse a key
-    dup = spconv.SparseConv3d(16, 16, 3, 2, 1, indice_key="down1").to(cuda_dev).half()
+    dup = spconv.SparseConv3d(32, 16, 3, 2, 1, indice_key="down1").to(cuda_dev).half()
     with pytest.raises(AssertionError, match="only support reuse subm indices"):
         dup(net[4](net[0](x)))
     # different algo on a shared key

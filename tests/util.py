@@ -1,5 +1,10 @@
 """Shared helpers for the parity tests (inputs are seeded numpy -> identical for CUDA and oracle)."""
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def random_cloud(rng, shape, num_per_batch, channels, dtype=np.float32):
@@ -15,31 +20,7 @@ def random_cloud(rng, shape, num_per_batch, channels, dtype=np.float32):
     return feats, indices
 
 
-def surface_cloud(rng, shape, n_target, batch=1):
-    """Spatially clustered voxels (random planar patches) ~6 neighbours/voxel like LiDAR data
-    (SURVEY 8d).  Returns unique int32 coords [N, 4], N <= n_target * batch."""
-    out = []
-    for b in range(batch):
-        pts = set()
-        D, H, W = shape
-        while len(pts) < n_target:
-            # a tilted planar patch
-            cz, cy, cx = rng.integers(0, D), rng.integers(0, H), rng.integers(0, W)
-            ext = int(rng.integers(8, 40))
-            sy, sx = rng.uniform(-0.3, 0.3, size=2)
-            ys = np.arange(max(0, cy - ext), min(H, cy + ext))
-            xs = np.arange(max(0, cx - ext), min(W, cx + ext))
-            yy, xx = np.meshgrid(ys, xs, indexing="ij")
-            zz = np.clip(np.round(cz + sy * (yy - cy) + sx * (xx - cx)).astype(np.int64), 0, D - 1)
-            keep = rng.random(yy.shape) < 0.85
-            for z, y, x in zip(zz[keep], yy[keep], xx[keep]):
-                pts.add((int(z), int(y), int(x)))
-                if len(pts) >= n_target:
-                    break
-        arr = np.array(sorted(pts), dtype=np.int32)
-        arr = arr[rng.permutation(arr.shape[0])]
-        out.append(np.concatenate([np.full((arr.shape[0], 1), b, np.int32), arr], axis=1))
-    return np.concatenate(out, 0)
+from bench_utils import surface_cloud  # noqa: E402,F401  (clustered LiDAR-like clouds)
 
 
 def rel_l2(a, b):
