@@ -265,23 +265,84 @@ def run_ours(args):
         allreduce(dw)
 
     # ---------------- e2e: public module API from pinned host buffers
-    def e2e_step(i):
-        c = clouds[i % NUM_CLOUDS]
-        d_inds = c["h_inds"].to(dev, non_blocking=True)
-        d_feats = c["h_feats"].to(dev, non_blocking=True).requires_grad_(True)
-        x = spconv.SparseConvTensor(d_feats, d_inds, wl["shape"], 1)
+    # Eager: every step copies this step's coordinates + features H2D, runs
+    # SparseConvTensor -> layer -> loss -> backward, and reads loss + dW back.
+    h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    h_dw = torch.zeros_like(weight, device="cpu").pin_memory()
+
+    def e2e_body(d_inds, d_feats):
+        xf = d_feats.detach().requires_grad_(True)
+        x = spconv.SparseConvTensor(xf, d_inds, wl["shape"], 1)
         layer.weight.grad = None
         y = layer(x)
-        loss = y.features.float().square().mean()
+        loss = y.features.square().mean(dtype=torch.float32)
         loss.backward()
+        return loss
+
+    def e2e_step_eager(i):
+        c = clouds[i % NUM_CLOUDS]
+        d_inds = c["h_inds"].to(dev, non_blocking=True)
+        d_feats = c["h_feats"].to(dev, non_blocking=True)
+        loss = e2e_body(d_inds, d_feats)
         allreduce(layer.weight.grad)
-        h_loss = loss.detach().to("cpu", non_blocking=True)
-        h_dw = layer.weight.grad.to("cpu", non_blocking=True)
-        return h_loss, h_dw
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        h_dw.copy_(layer.weight.grad, non_blocking=True)
 
     for i in range(3):
-        e2e_step(i)
+        e2e_step_eager(i)
     torch.cuda.synchronize()
+
+    # Graph-captured e2e step with double buffering: the replay of step i computes on device
+    # buffer i%2 and, on a forked stream inside the same graph, copies the NEXT cloud H2D into
+    # buffer (i+1)%2 -- so every timed step still contains one full H2D of a step's inputs and
+    # the D2H of its results, but the copy overlaps the kernels.
+    e2e_graphs = None
+    if use_graph:
+        try:
+            n_max = max(c["n"] for c in clouds)
+            bufs = [dict(inds=torch.empty((n_max, 4), dtype=torch.int32, device=dev),
+                         feats=torch.empty((n_max, C), dtype=tdt, device=dev)) for _ in range(2)]
+            side = torch.cuda.Stream()
+            e2e_graphs = []
+            for j, c in enumerate(clouds):
+                cur, nxt = bufs[j % 2], bufs[(j + 1) % 2]
+                cn = clouds[(j + 1) % NUM_CLOUDS]
+                cur["inds"][:c["n"]].copy_(c["h_inds"])
+                cur["feats"][:c["n"]].copy_(c["h_feats"])
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    main = torch.cuda.current_stream()
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        nxt["inds"][:cn["n"]].copy_(cn["h_inds"], non_blocking=True)
+                        nxt["feats"][:cn["n"]].copy_(cn["h_feats"], non_blocking=True)
+                    loss = e2e_body(cur["inds"][:c["n"]], cur["feats"][:c["n"]])
+                    if world == 1:
+                        h_loss.copy_(loss.detach(), non_blocking=True)
+                        h_dw.copy_(layer.weight.grad, non_blocking=True)
+                    main.wait_stream(side)
+                e2e_graphs.append((g, loss))
+            torch.cuda.synchronize()
+            # prologue: cloud 0 must be resident in buffer 0 before the first replay
+            bufs[0]["inds"][:clouds[0]["n"]].copy_(clouds[0]["h_inds"])
+            bufs[0]["feats"][:clouds[0]["n"]].copy_(clouds[0]["h_feats"])
+            torch.cuda.synchronize()
+        except Exception as e:
+            print(f"[bench] e2e CUDA-graph capture failed ({type(e).__name__}: {e}); e2e runs eagerly",
+                  file=sys.stderr)
+            e2e_graphs = None
+            torch.cuda.synchronize()
+
+    def e2e_step(i):
+        if e2e_graphs is None:
+            return e2e_step_eager(i)
+        g, loss = e2e_graphs[i % NUM_CLOUDS]
+        g.replay()
+        if world > 1:
+            allreduce(layer.weight.grad)
+            h_loss.copy_(loss.detach(), non_blocking=True)
+            h_dw.copy_(layer.weight.grad, non_blocking=True)
 
     # kernels of THIS library per step (graph replays re-issue exactly the captured launches)
     ops.launch_count(reset=True)
@@ -295,6 +356,7 @@ def run_ours(args):
     ms_value = timed_loop(value_step, args.steps)
     launches = launches_per_step * args.steps
     ms_e2e = timed_loop(e2e_step, args.steps)
+    ms_e2e_eager = timed_loop(e2e_step_eager, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---------------- per-kernel timing for the roofline (events around every C-ABI region)
@@ -306,12 +368,13 @@ def run_ours(args):
     regions = {k: v / reps for k, v in timer.get_all_pair_time().items()}
 
     # ---------------- reduce over ranks (max time, sum voxels)
-    t_value = torch.tensor([float(np.mean(ms_value)), float(np.mean(ms_e2e))], device=dev, dtype=torch.float64)
+    t_value = torch.tensor([float(np.mean(ms_value)), float(np.mean(ms_e2e)), float(np.mean(ms_e2e_eager))],
+                           device=dev, dtype=torch.float64)
     n_total = torch.tensor([n_per_step], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_value, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_total, op=dist.ReduceOp.SUM)
-    ms_step, ms_step_e2e = float(t_value[0]), float(t_value[1])
+    ms_step, ms_step_e2e, ms_step_e2e_eager = float(t_value[0]), float(t_value[1]), float(t_value[2])
     voxels = float(n_total[0])
 
     if rank == 0:
@@ -358,7 +421,11 @@ def run_ours(args):
             "e2e": {"value": voxels / (ms_step_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": int(c0["h_inds"].numel() * 4 + c0["h_feats"].numel() * elem),
                     "d2h_bytes_per_step": int(weight.numel() * elem + 4),
-                    "api": "SparseConvTensor -> SubMConv3d.forward -> loss.backward (pinned host in, loss+dW out)"},
+                    "api": "SparseConvTensor -> SubMConv3d.forward -> loss.backward (pinned host in, loss+dW out)",
+                    "cuda_graph": e2e_graphs is not None,
+                    "overlap": "H2D of the next cloud on a forked stream inside the step's graph"
+                               if e2e_graphs is not None else "none",
+                    "eager_value": voxels / (ms_step_e2e_eager * 1e-3), "eager_ms_per_step": ms_step_e2e_eager},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernel_ms": {k: round(v, 4) for k, v in sorted(regions.items())},

@@ -125,8 +125,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// Spin on try_wait (which itself suspends in hardware for a while).  A protocol bug must become
+// an error, not a hung GPU: after ~2 s of waiting the kernel traps (cudaErrorLaunchFailure).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFFu) == 0u && clock64() - t0 > 4000000000ll) {
+            printf("spconv_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
 }
 // arrive (no pending-count increment) once all prior cp.async of this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {

@@ -27,9 +27,11 @@
 namespace spx {
 
 constexpr int TC_TILE_M = 128;
-constexpr int TC_THREADS = 288;          // warps 0-3 epilogue | 4-7 gather producers | 8 MMA issuer
+constexpr int TC_THREADS = 320;          // warps 0-3 epilogue | 4-7 gather producers | 8 MMA issuer | 9 TMA + index copies
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_CTAS_PER_SM = 2;        // two resident CTAs per SM: every role is a latency-bound single warp
+constexpr int TC_SMEM_BUDGET_2 = 104 * 1024;   // per CTA when two CTAs share an SM
+constexpr int TC_SMEM_BUDGET = 200 * 1024;     // per CTA when a tile needs the whole SM
 
 struct TcParams {
     // gathered operand A
@@ -44,7 +46,7 @@ struct TcParams {
     int span_b_elems;       // span_b / elem bytes
     int n;                  // UMMA N (output channels of this pass)
     uint32_t idesc;
-    int stages, a_stage_bytes, stage_bytes, idx_bytes;
+    int stages, a_stage_bytes, stage_bytes, idx_bytes, ctas_per_sm;
     uint32_t tmem_cols;
     // rows
     int64_t rows;
@@ -63,19 +65,15 @@ struct TcParams {
     float output_add_scale;
 };
 
-// iterate set bits of a <=128-bit tile mask in ascending order
+// iterate set bits of a <=128-bit tile mask in ascending order (register-only: no indexed array)
 struct BitIter {
-    uint32_t m[4];
-    int w;
+    uint32_t m0, m1, m2, m3;
+    __device__ __forceinline__ BitIter(const uint32_t (&t)[4]) : m0(t[0]), m1(t[1]), m2(t[2]), m3(t[3]) {}
     __device__ __forceinline__ int next() {
-        while (w < 4) {
-            if (m[w]) {
-                int b = __ffs(m[w]) - 1;
-                m[w] &= m[w] - 1;
-                return w * 32 + b;
-            }
-            ++w;
-        }
+        if (m0) { int b = __ffs(m0) - 1; m0 &= m0 - 1; return b; }
+        if (m1) { int b = __ffs(m1) - 1; m1 &= m1 - 1; return 32 + b; }
+        if (m2) { int b = __ffs(m2) - 1; m2 &= m2 - 1; return 64 + b; }
+        if (m3) { int b = __ffs(m3) - 1; m3 &= m3 - 1; return 96 + b; }
         return -1;
     }
 };
@@ -185,7 +183,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t t_row,
 }
 
 template <int KIND, int CPR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
     constexpr int LG_CPR = CPR == 2 ? 1 : CPR == 4 ? 2 : CPR == 8 ? 3 : CPR == 16 ? 4 : 5;
     constexpr int RPI = 32 / CPR;            // rows covered by one warp-wide cp.async instruction
@@ -242,8 +240,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     if (warp >= 4 && warp < 8) {
         // ================================================= gather producers
         const int pw = warp - 4;
-        const bool leader = (pw == 0 && lane == 0);
-        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
         // per-lane constants: chunk ch of rows r0 + itc*RPI (itc = 0..CPR-1) of this warp's 32 rows
         const int r0 = lane >> LG_CPR;
         const uint32_t byte_in_row = (uint32_t)(lane & (CPR - 1)) << 4;
@@ -259,32 +255,17 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         int stage = 0; uint32_t phase = 0;
         int64_t local = 0;
         int64_t tile = blockIdx.x;
-        // the gather-index block of tile t+1 is bulk-copied while tile t is being gathered
-        auto fetch_indices = [&](int64_t t, int64_t lcl) {
-            const int b = (int)(lcl & 1);
-            const uint32_t use = (uint32_t)(lcl >> 1);
-            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
-            bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
-                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
-        };
         uint32_t tm[4] = {0, 0, 0, 0};
-        if (tile < num_tiles) {
-            if (leader) fetch_indices(tile, 0);
-            load_tile_mask(p.tile_mask, tile, p.words, tm);
-        }
+        if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
         for (; tile < num_tiles; tile += gridDim.x, ++local) {
             const int buf = (int)(local & 1);
             const int64_t next = tile + gridDim.x;
             uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (next < num_tiles) {
-                load_tile_mask(p.tile_mask, next, p.words, tm_next);
-                if (leader) fetch_indices(next, local + 1);
-            }
+            if (next < num_tiles) load_tile_mask(p.tile_mask, next, p.words, tm_next);
             mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
             const int32_t *idx_lane = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes) +
                                       pw * 32 + r0;
-            BitIter it{{tm[0], tm[1], tm[2], tm[3]}, 0};
+            BitIter it(tm);
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&empty[stage], phase ^ 1u);
                 const uint32_t a_stage = smem_base + (uint32_t)stage * p.stage_bytes;
@@ -296,17 +277,58 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
                     cp_async_16(a_stage + dst_off[itc], src, ridx >= 0 ? 16u : 0u);
                 }
                 cp_async_mbar_arrive_noinc(&full[stage]);
-                if (leader) {
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            mbar_arrive(&idx_empty[buf]);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
+        }
+    } else if (warp == 9) {
+        // ================================================= TMA warp: weight boxes + gather-index blocks
+        // all 32 lanes walk the loops together (the CTA-wide barrier at the end must be reached
+        // convergently); lane 0 issues the copies
+        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
+        // the gather-index block of tile t+1 is bulk-copied while tile t is being gathered
+        auto fetch_indices = [&](int64_t t, int64_t lcl) {
+            const int b = (int)(lcl & 1);
+            const uint32_t use = (uint32_t)(lcl >> 1);
+            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
+                bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
+                              p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
+            }
+            __syncwarp();
+        };
+        int stage = 0; uint32_t phase = 0;
+        int64_t local = 0;
+        int64_t tile = blockIdx.x;
+        uint32_t tm[4] = {0, 0, 0, 0};
+        if (tile < num_tiles) {
+            fetch_indices(tile, 0);
+            load_tile_mask(p.tile_mask, tile, p.words, tm);
+        }
+        for (; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int64_t next = tile + gridDim.x;
+            uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (next < num_tiles) {
+                load_tile_mask(p.tile_mask, next, p.words, tm_next);
+                fetch_indices(next, local + 1);
+            }
+            BitIter it(tm);
+            for (int k = it.next(); k >= 0; k = it.next()) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                if (lane == 0) {
                     const int kw = p.reverse ? p.kv - 1 - k : k;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)p.b_bytes);
-                    const uint32_t b_stage = a_stage + p.a_stage_bytes;
+                    const uint32_t b_stage = smem_base + (uint32_t)stage * p.stage_bytes + p.a_stage_bytes;
                     for (int sb = 0; sb < p.b_subtiles; ++sb)
                         tma_load_2d(b_stage + sb * p.b_sub_bytes, &tmap_w, &full[stage],
                                     kw * p.w_inner_elems + sb * p.span_b_elems, 0);
                 }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            mbar_arrive(&idx_empty[buf]);
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
@@ -331,7 +353,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n);
-            BitIter it{{tm[0], tm[1], tm[2], tm[3]}, 0};
+            BitIter it(tm);
             uint32_t accumulate = 0;
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&full[stage], phase);
@@ -514,12 +536,15 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.a_stage_bytes = (int)align_up((size_t)TC_TILE_M * p.xb, 1024);
     p.stage_bytes = p.a_stage_bytes + (int)align_up((size_t)p.b_bytes, 1024);
     p.idx_bytes = (int)align_up((size_t)(a.kv + 1) * 512, 1024);
-    p.stages = (TC_SMEM_BUDGET - 2 * p.idx_bytes) / p.stage_bytes;
-    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-    SPX_REQUIRE(p.stages >= 2, "tc_gather_gemm: tile does not fit shared memory (stage %d bytes)", p.stage_bytes);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * cy)) cols <<= 1;
     p.tmem_cols = cols;
+    // two CTAs per SM when >= 3 pipeline stages and both TMEM allocations fit; else one big CTA
+    p.ctas_per_sm = ((TC_SMEM_BUDGET_2 - 2 * p.idx_bytes) / p.stage_bytes >= 3 && cols <= 256) ? TC_CTAS_PER_SM : 1;
+    const int budget = p.ctas_per_sm == 2 ? TC_SMEM_BUDGET_2 : TC_SMEM_BUDGET;
+    p.stages = (budget - 2 * p.idx_bytes) / p.stage_bytes;
+    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+    SPX_REQUIRE(p.stages >= 2, "tc_gather_gemm: tile does not fit shared memory (stage %d bytes)", p.stage_bytes);
     p.rows = a.rows; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask; p.argsort = a.argsort;
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
@@ -533,10 +558,12 @@ static int launch_tc_cpr(const CUtensorMap &tm, const TcParams &p, cudaStream_t 
     if (!configured) {
         SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(TC_SMEM_BUDGET + 2048)));
+        SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
     const int64_t tiles = div_up64(p.rows, TC_TILE_M);
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    const int64_t max_ctas = (int64_t)sm_count() * p.ctas_per_sm;
+    const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
     tc_gather_gemm_kernel<KIND, CPR><<<grid, TC_THREADS, smem, stream>>>(tm, p);
     SPX_CHECK_LAUNCH("tc_gather_gemm_kernel");
     return 0;

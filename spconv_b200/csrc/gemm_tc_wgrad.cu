@@ -17,7 +17,10 @@
 namespace spx {
 
 constexpr int WG_TILE = 128;
-constexpr int WG_THREADS = 288;          // warps 0-3 epilogue | 4-7 producers | 8 MMA issuer
+constexpr int WG_PROD_WARPS = 8;        // 16 tile rows per producer warp
+constexpr int WG_PROD_THREADS = WG_PROD_WARPS * 32;
+constexpr int WG_MMA_WARP = 4 + WG_PROD_WARPS;
+constexpr int WG_THREADS = (WG_MMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 producers | 12 MMA issuer
 constexpr int WG_MAX_STAGES = 6;
 constexpr int WG_SMEM_BUDGET = 200 * 1024;
 
@@ -58,6 +61,8 @@ tc_wgrad_kernel(const WgParams p) {
     constexpr int RPI = 32 / CPA;
     constexpr int SPAN_X = CPA * 16;
     constexpr int LG_SPAN_X = LG_CPA + 4;
+    constexpr int ROWS_PW = WG_TILE / WG_PROD_WARPS;           // tile rows per producer warp
+    constexpr int ITERS = ROWS_PW / RPI > 0 ? ROWS_PW / RPI : 1;   // cp.async per thread per atom
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -86,16 +91,16 @@ tc_wgrad_kernel(const WgParams p) {
     const int g_end = min(p.groups_total, g_begin + p.groups_per_pass);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], WG_PROD_THREADS); mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&full_b[b], 128); mbar_init(&empty_b[b], 1);
-            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], 128);
+            mbar_init(&full_b[b], WG_PROD_THREADS); mbar_init(&empty_b[b], 1);
+            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], WG_PROD_THREADS);
         }
         mbar_init(acc_done, 1);
         *used_smem = 0;
         mbar_fence_init();
     }
-    if (warp == 8) {
+    if (warp == WG_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -105,7 +110,7 @@ tc_wgrad_kernel(const WgParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < WG_MMA_WARP) {
         // ================================================= producers
         const int pw = warp - 4;
         const bool leader = (pw == 0 && lane == 0);
@@ -117,10 +122,10 @@ tc_wgrad_kernel(const WgParams p) {
         const int r0 = lane >> LG_CPA;
         const uint32_t chb = (uint32_t)(lane & (CPA - 1)) << 4;
         const uint8_t *x_lane = p.x + chb;
-        uint32_t dst_off[CPA];
+        uint32_t dst_off[ITERS];
 #pragma unroll
-        for (int itc = 0; itc < CPA; ++itc)
-            dst_off[itc] = swizzle_offset(((uint32_t)(pw * 32 + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
+        for (int itc = 0; itc < ITERS; ++itc)
+            dst_off[itc] = swizzle_offset(((uint32_t)(pw * ROWS_PW + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
         const int lg_apo = p.apo == 1 ? 0 : (p.apo == 2 ? 1 : 2);
         auto fetch_indices = [&](int64_t t, int64_t lcl) {
             const int b = (int)(lcl & 1);
@@ -155,15 +160,15 @@ tc_wgrad_kernel(const WgParams p) {
                     const int bb = (int)(nb & 1);
                     mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
                     const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
-                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * 32;
-                    for (int itc = 0; itc < cpr_d; ++itc) {
+                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW;
+                    for (int itc = 0; itc * 32 < ROWS_PW * cpr_d; ++itc) {
                         const int flat = itc * 32 + lane;
                         const int r = flat >> p.lg_cpr_d;
                         const uint32_t byte_in_row = (uint32_t)(flat & (cpr_d - 1)) << 4;
                         const int32_t rsrc = rows_s[r];
                         const uint32_t sub = byte_in_row >> p.lg_span_d;
                         const uint32_t within = byte_in_row & (uint32_t)(p.span_d - 1);
-                        const uint32_t row_in_tile = (uint32_t)(pw * 32 + r);
+                        const uint32_t row_in_tile = (uint32_t)(pw * ROWS_PW + r);
                         const uint32_t dst = dstb + sub * (uint32_t)(WG_TILE * p.span_d) +
                                              swizzle_offset((row_in_tile << p.lg_span_d) + within, p.span_d);
                         const uint8_t *src = p.d + (rsrc >= 0 ? (int64_t)rsrc * p.db + byte_in_row : 0);
@@ -182,11 +187,11 @@ tc_wgrad_kernel(const WgParams p) {
                         const int k = a >> lg_apo;
                         const int cb = a & (p.apo - 1);
                         const bool active = k < p.kv && bit_set(tm, k);
-                        const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * 32 + r0;
+                        const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * ROWS_PW + r0;
                         const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * SPAN_X);
                         const uint8_t *x_atom = x_lane + cb * SPAN_X;
 #pragma unroll
-                        for (int itc = 0; itc < CPA; ++itc) {
+                        for (int itc = 0; itc < ITERS; ++itc) {
                             const int32_t ridx = active ? idx_k[itc * RPI] : -1;
                             cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx, 0) * p.xb,
                                         ridx >= 0 ? 16u : 0u);
@@ -200,7 +205,7 @@ tc_wgrad_kernel(const WgParams p) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
-    } else if (warp == 8) {
+    } else if (warp == WG_MMA_WARP) {
         // ================================================= MMA issuer
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;
@@ -292,7 +297,7 @@ tc_wgrad_kernel(const WgParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == WG_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }

@@ -836,8 +836,15 @@ extern "C" int spx_pairs_to_table(const int32_t *pairs, const int32_t *indice_pa
     return 0;
 }
 
+namespace spx {
+size_t radix_argsort_workspace_bytes(int64_t n);
+int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+}
+
 extern "C" size_t spx_mask_argsort_workspace_size(int64_t N, int words) {
     if (N <= 0) return 256;
+    if (words == 1) return radix_argsort_workspace_bytes(N);
     size_t n = (size_t)N;
     return 4 * align_up(n * 4, 256) + align_up(n * 4 * (size_t)words, 256) + align_up(sort_pairs_temp_bytes(N), 256) + 1024;
 }
@@ -855,6 +862,8 @@ extern "C" int spx_mask_argsort(uint32_t *mask, int32_t *argsort, int64_t N, int
         return 0;
     }
     SPX_REQUIRE(workspace != nullptr, "workspace is NULL");
+    if (words == 1)   // hand-written 9-bit-digit stable radix argsort (sort.cu)
+        return radix_argsort(mask, argsort, N, kv > 0 && kv < 32 ? kv : 32, workspace, workspace_bytes, stream);
     WorkspaceCarver ws(workspace, workspace_bytes);
     uint32_t *keys_in = ws.take<uint32_t>(N);
     uint32_t *keys_out = ws.take<uint32_t>(N);

@@ -1,0 +1,217 @@
+// Stable LSD radix argsort of the 32-bit neighbour masks (one mask word, kv <= 32).
+//
+// Reference: thrust::sort_by_key on the masks with an iota payload
+// (spconv/csrc/sparse/all.py:935-1000).  For the rulebook sizes of this path (1e5..1e6 keys) a
+// library radix sort is launch/latency-bound: CUB's onesweep spends ~12 us per 8-bit pass plus
+// histogram/scan kernels (~80 us for 100 k keys, measured on B200).  This version uses 9-bit
+// digits (3 passes for the 27-bit masks of a 3x3x3 kernel instead of 4), two small kernels per
+// pass, and nothing else:
+//   hist    : per-block digit histogram -> counts[digit][block]
+//   scatter : every block derives its global digit bases from `counts` (no separate scan kernel
+//             for <= 256 blocks), ranks its keys stably with warp match_any, and scatters.
+// The first pass reads the masks with an implicit iota payload, the last pass writes the sorted
+// masks back in place (thrust semantics) and the argsort.
+#include "common.cuh"
+
+namespace spx {
+
+constexpr int RS_BITS = 9;
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 4;                        // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // keys per block
+constexpr int RS_FUSED_MAX_BLOCKS = 256;           // above this a scan kernel computes the bases
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int *__restrict__ counts) {
+    __shared__ int hist[RS_BINS];
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) hist[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int64_t i = base + j * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (RS_BINS - 1)], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) counts[(int64_t)d * nblk + blockIdx.x] = hist[d];
+}
+
+// large inputs only: counts[d][b] -> exclusive prefix over b, totals[d] = sum_b
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals) {
+    const int d = blockIdx.x;
+    __shared__ int warp_sums[RS_WARPS];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblk; b0 += RS_THREADS) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nblk ? counts[(int64_t)d * nblk + b] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warp_sums[w];
+        const int carry = carry_s;
+        if (b < nblk) counts[(int64_t)d * nblk + b] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == RS_THREADS - 1) carry_s = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[d] = carry_s;
+}
+
+// FUSED: bases are summed from raw counts by every block; else counts already hold block prefixes
+template <bool FUSED, bool IOTA_IN>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
+                  int nblk, const int *__restrict__ counts, const int *__restrict__ totals,
+                  uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
+    __shared__ int digit_base[RS_BINS];             // global position of this block's first key of each digit
+    __shared__ int warp_cnt[RS_WARPS][RS_BINS];     // running per-warp digit counts -> warp bases
+    __shared__ int scan_tmp[RS_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk = blockIdx.x;
+
+    // ---- (1) per-digit: total over all blocks and the part before this block
+    int my_total[RS_BINS / RS_THREADS], my_before[RS_BINS / RS_THREADS];
+#pragma unroll
+    for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+        const int d = q * RS_THREADS + tid;
+        if (FUSED) {
+            int tot = 0, before = 0;
+            const int *row = counts + (int64_t)d * nblk;
+            for (int b = 0; b < nblk; ++b) {
+                const int c = __ldg(row + b);
+                tot += c;
+                if (b < blk) before += c;
+            }
+            my_total[q] = tot; my_before[q] = before;
+        } else {
+            my_total[q] = __ldg(totals + d);
+            my_before[q] = __ldg(counts + (int64_t)d * nblk + blk);
+        }
+    }
+    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
+    // exclusive scan of the 512 digit totals (digit d = q*256 + tid; q-major order keeps d ascending)
+    int run = 0;
+#pragma unroll
+    for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+        int v = my_total[q], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) scan_tmp[warp] = incl;
+        __syncthreads();
+        int wbase = 0, all = 0;
+        for (int w = 0; w < RS_WARPS; ++w) { if (w < warp) wbase += scan_tmp[w]; all += scan_tmp[w]; }
+        digit_base[q * RS_THREADS + tid] = run + wbase + incl - v + my_before[q];
+        run += all;
+        __syncthreads();
+    }
+
+    // ---- (2) stable rank inside the block: warp w owns keys [w*128, w*128+128) of the tile, 4 rounds of 32
+    const int64_t tile_base = (int64_t)blk * RS_TILE + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS];
+    int32_t val[RS_ITEMS];
+    int rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = tile_base + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0xffffffffu;
+        val[r] = ok ? (IOTA_IN ? (int32_t)i : vals_in[i]) : -1;
+        const int d = ok ? (int)((key[r] >> shift) & (RS_BINS - 1)) : RS_BINS;   // RS_BINS = "no key"
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        int old = 0;
+        if (ok && lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- (3) warp bases: exclusive scan over warps per digit (in place)
+    for (int d = tid; d < RS_BINS; d += RS_THREADS) {
+        int acc = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const int c = warp_cnt[w][d]; warp_cnt[w][d] = acc; acc += c; }
+    }
+    __syncthreads();
+    // ---- (4) scatter
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = tile_base + r * 32 + lane;
+        if (i < n) {
+            const int d = (int)((key[r] >> shift) & (RS_BINS - 1));
+            const int pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+size_t radix_argsort_workspace_bytes(int64_t n) {
+    const int64_t nblk = div_up64(n > 0 ? n : 1, RS_TILE);
+    return 4 * align_up((size_t)n * 4, 256) + align_up((size_t)RS_BINS * nblk * 4, 256) + align_up(RS_BINS * 4, 256) + 1024;
+}
+
+// keys: mask [n] (sorted in place on return), argsort [n] out.  Returns 0 / error code.
+int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+    if (n == 0) return 0;
+    WorkspaceCarver ws(workspace, workspace_bytes);
+    uint32_t *keys_a = ws.take<uint32_t>(n);
+    int32_t *vals_a = ws.take<int32_t>(n);
+    uint32_t *keys_b = ws.take<uint32_t>(n);
+    int32_t *vals_b = ws.take<int32_t>(n);
+    const int nblk = (int)div_up64(n, RS_TILE);
+    int *counts = ws.take<int>((size_t)RS_BINS * nblk);
+    int *totals = ws.take<int>(RS_BINS);
+    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 32) key_bits = 32;
+    const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    const bool fused = nblk <= RS_FUSED_MAX_BLOCKS;
+    const uint32_t *kin = mask;
+    const int32_t *vin = nullptr;
+    for (int pass = 0; pass < passes; ++pass) {
+        const bool last = pass == passes - 1;
+        uint32_t *kout = (pass & 1) ? keys_b : keys_a;
+        int32_t *vout = (pass & 1) ? vals_b : vals_a;
+        if (last && pass > 0) { kout = mask; vout = argsort; }      // never aliases kin (kin is a scratch buffer)
+        const int shift = pass * RS_BITS;
+        rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, shift, nblk, counts);
+        SPX_CHECK_LAUNCH("rs_hist_kernel");
+        if (!fused) {
+            rs_scan_kernel<<<RS_BINS, RS_THREADS, 0, stream>>>(counts, nblk, totals);
+            SPX_CHECK_LAUNCH("rs_scan_kernel");
+        }
+        if (pass == 0) {
+            if (fused) rs_scatter_kernel<true, true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
+            else rs_scatter_kernel<false, true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
+        } else {
+            if (fused) rs_scatter_kernel<true, false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
+            else rs_scatter_kernel<false, false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
+        }
+        SPX_CHECK_LAUNCH("rs_scatter_kernel");
+        kin = kout; vin = vout;
+    }
+    if (passes == 1) {   // single pass wrote to scratch: copy back
+        SPX_CHECK_CUDA(cudaMemcpyAsync(mask, keys_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        SPX_CHECK_CUDA(cudaMemcpyAsync(argsort, vals_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return 0;
+}
+
+}  // namespace spx
