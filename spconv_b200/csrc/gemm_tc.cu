@@ -23,13 +23,18 @@
 #include "gemm.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace spx {
 
 constexpr int TC_TILE_M = 128;
-constexpr int TC_THREADS = 320;          // warps 0-3 epilogue | 4-7 gather producers | 8 MMA issuer | 9 TMA + index copies
+constexpr int TC_PROD_WARPS = 8;         // 16 tile rows per producer warp
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+constexpr int TC_MMA_WARP = 4 + TC_PROD_WARPS;
+constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;
+constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 gather producers | 12 MMA issuer | 13 TMA + index copies
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_CTAS_PER_SM = 2;        // two resident CTAs per SM: every role is a latency-bound single warp
+constexpr int TC_CTAS_PER_SM = 1;        // the clock64 timeline shows pipeline DEPTH matters most: one CTA, all smem as stages
 constexpr int TC_SMEM_BUDGET_2 = 104 * 1024;   // per CTA when two CTAs share an SM
 constexpr int TC_SMEM_BUDGET = 200 * 1024;     // per CTA when a tile needs the whole SM
 
@@ -63,6 +68,8 @@ struct TcParams {
     const float *scale, *bias_f32;
     const int8_t *output_add;
     float output_add_scale;
+    long long *dbg_ts;      // optional [4 roles][2048] clock64 stamps of CTA 0 (SPX_TC_TRACE, perf triage)
+    int debug;              // SPX_TC_DEBUG ablation bits (perf triage only): 1 no gather, 2 no MMA, 4 no epilogue, 8 no weight TMA
 };
 
 // iterate set bits of a <=128-bit tile mask in ascending order (register-only: no indexed array)
@@ -182,6 +189,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t t_row,
     }
 }
 
+#define TC_STAMP(role, n) do { if (p.dbg_ts && blockIdx.x == 0 && lane == 0 && (n) < 2048) p.dbg_ts[(role) * 2048 + (n)] = clock64(); } while (0)
+
 template <int KIND, int CPR>
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
@@ -191,6 +200,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     constexpr int SPAN_A = XB < 128 ? XB : 128;
     constexpr int LG_SPAN_A = SPAN_A == 128 ? 7 : (SPAN_A == 64 ? 6 : 5);
     constexpr int A_SUB_BYTES = TC_TILE_M * SPAN_A;
+    constexpr int ROWS_PW = TC_TILE_M / TC_PROD_WARPS;          // tile rows per producer warp
+    constexpr int ITERS = ROWS_PW / RPI > 0 ? ROWS_PW / RPI : 1;  // cp.async per thread per stage
+    static_assert(ROWS_PW * CPR >= 32, "a producer warp must cover at least one full cp.async instruction");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: align manually to 1024
@@ -208,6 +220,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     uint64_t *idx_full = bars + 2 * TC_MAX_STAGES + 4;    // [2] bulk copy -> producers
     uint64_t *idx_empty = bars + 2 * TC_MAX_STAGES + 6;   // [2] producers -> bulk copy
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 8);
+    // per (stage, k-step) UMMA descriptor pairs, built once: the issuing thread only loads and fires
+    uint4 *desc_tab = reinterpret_cast<uint4 *>(bars + 2 * TC_MAX_STAGES + 10);   // [stages][16]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -215,44 +229,64 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], 128 + 1);    // 128 cp.async arrivals + 1 expect_tx arrival
+            mbar_init(&full[s], TC_PROD_THREADS + 1);    // cp.async arrivals + 1 expect_tx arrival
             mbar_init(&empty[s], 1);         // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
             mbar_init(&idx_full[a], 1);      // expect_tx arrival of the bulk copy
-            mbar_init(&idx_empty[a], 128);   // every producer thread releases the buffer
+            mbar_init(&idx_empty[a], TC_PROD_THREADS);   // every producer thread releases the buffer
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap_w);
     }
-    if (warp == 8) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        const int ksteps = p.a_subtiles * p.q_a;
+        const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
+        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
+                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
+        for (int e = lane; e < p.stages * 16; e += 32) {
+            const int st = e >> 4, j = e & 15;
+            if (j < ksteps) {
+                const uint32_t a16 = (smem_base + (uint32_t)st * p.stage_bytes) >> 4;
+                const uint32_t b16 = a16 + ((uint32_t)p.a_stage_bytes >> 4);
+                const uint32_t sub = (uint32_t)(j / p.q_a), jr = (uint32_t)(j % p.q_a);
+                const uint64_t ad = a_hi | (uint64_t)((a16 + sub * (uint32_t)(A_SUB_BYTES >> 4) + 2u * jr) & 0x3FFFu);
+                uint32_t boff;
+                if (!p.b_mn_major) boff = sub * ((uint32_t)p.b_sub_bytes >> 4) + 2u * jr;   // same contraction walk as A
+                else boff = (uint32_t)j * (uint32_t)p.b_kstep16_mn;                         // k-step = UMMA_K weight rows
+                const uint64_t bd = b_hi | (uint64_t)((b16 + boff) & 0x3FFFu);
+                desc_tab[e] = make_uint4((uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32));
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp == 0) TC_STAMP(3, 0);
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < TC_MMA_WARP) {
         // ================================================= gather producers
         const int pw = warp - 4;
         // per-lane constants: chunk ch of rows r0 + itc*RPI (itc = 0..CPR-1) of this warp's 32 rows
         const int r0 = lane >> LG_CPR;
         const uint32_t byte_in_row = (uint32_t)(lane & (CPR - 1)) << 4;
         const uint8_t *x_lane = p.x + byte_in_row;
-        uint32_t dst_off[CPR];
+        uint32_t dst_off[ITERS];
 #pragma unroll
-        for (int itc = 0; itc < CPR; ++itc) {
-            const uint32_t row_in_tile = (uint32_t)(pw * 32 + r0 + itc * RPI);
+        for (int itc = 0; itc < ITERS; ++itc) {
+            const uint32_t row_in_tile = (uint32_t)(pw * ROWS_PW + r0 + itc * RPI);
             const uint32_t sub = byte_in_row >> LG_SPAN_A;
             const uint32_t within = byte_in_row & (uint32_t)(SPAN_A - 1);
             dst_off[itc] = sub * (uint32_t)A_SUB_BYTES + swizzle_offset((row_in_tile << LG_SPAN_A) + within, SPAN_A);
         }
         int stage = 0; uint32_t phase = 0;
+        int nstamp = 0;
         int64_t local = 0;
         int64_t tile = blockIdx.x;
         uint32_t tm[4] = {0, 0, 0, 0};
@@ -264,26 +298,31 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             if (next < num_tiles) load_tile_mask(p.tile_mask, next, p.words, tm_next);
             mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
             const int32_t *idx_lane = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes) +
-                                      pw * 32 + r0;
+                                      pw * ROWS_PW + r0;
             BitIter it(tm);
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&empty[stage], phase ^ 1u);
+                if (pw == 0) TC_STAMP(0, 2 * nstamp);
                 const uint32_t a_stage = smem_base + (uint32_t)stage * p.stage_bytes;
                 const int32_t *idx_k = idx_lane + k * 128;
+                if (!(p.debug & 1)) {
 #pragma unroll
-                for (int itc = 0; itc < CPR; ++itc) {
-                    const int32_t ridx = idx_k[itc * RPI];
-                    const uint8_t *src = x_lane + (int64_t)max(ridx, 0) * XB;
-                    cp_async_16(a_stage + dst_off[itc], src, ridx >= 0 ? 16u : 0u);
+                    for (int itc = 0; itc < ITERS; ++itc) {
+                        const int32_t ridx = idx_k[itc * RPI];
+                        const uint8_t *src = x_lane + (int64_t)max(ridx, 0) * XB;
+                        cp_async_16(a_stage + dst_off[itc], src, ridx >= 0 ? 16u : 0u);
+                    }
                 }
                 cp_async_mbar_arrive_noinc(&full[stage]);
+                if (pw == 0) TC_STAMP(0, 2 * nstamp + 1);
+                ++nstamp;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             mbar_arrive(&idx_empty[buf]);
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
-    } else if (warp == 9) {
+    } else if (warp == TC_TMA_WARP) {
         // ================================================= TMA warp: weight boxes + gather-index blocks
         // all 32 lanes walk the loops together (the CTA-wide barrier at the end must be reached
         // convergently); lane 0 issues the copies
@@ -320,11 +359,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
                 mbar_wait(&empty[stage], phase ^ 1u);
                 if (lane == 0) {
                     const int kw = p.reverse ? p.kv - 1 - k : k;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)p.b_bytes);
-                    const uint32_t b_stage = smem_base + (uint32_t)stage * p.stage_bytes + p.a_stage_bytes;
-                    for (int sb = 0; sb < p.b_subtiles; ++sb)
-                        tma_load_2d(b_stage + sb * p.b_sub_bytes, &tmap_w, &full[stage],
-                                    kw * p.w_inner_elems + sb * p.span_b_elems, 0);
+                    if (p.debug & 8) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], (uint32_t)p.b_bytes);
+                        const uint32_t b_stage = smem_base + (uint32_t)stage * p.stage_bytes + p.a_stage_bytes;
+                        for (int sb = 0; sb < p.b_subtiles; ++sb)
+                            tma_load_2d(b_stage + sb * p.b_sub_bytes, &tmap_w, &full[stage],
+                                        kw * p.w_inner_elems + sb * p.span_b_elems, 0);
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -332,18 +375,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_MMA_WARP) {
         // ================================================= MMA issuer
+        int nstamp = 0;
         int stage = 0; uint32_t phase = 0;
         int64_t local = 0;
         int64_t tile = blockIdx.x;
         uint32_t tm[4] = {0, 0, 0, 0};
         if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
-        // loop-invariant descriptor pieces (descriptor = high part | (address >> 4))
-        const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
-        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
-                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
-        const uint32_t b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
+        const int ksteps = p.a_subtiles * p.q_a;
         for (; tile < num_tiles; tile += gridDim.x, ++local) {
             const int64_t next = tile + gridDim.x;
             uint32_t tm_next[4] = {0, 0, 0, 0};
@@ -357,39 +397,24 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             uint32_t accumulate = 0;
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                fence_proxy_async_smem();
+                TC_STAMP(1, 2 * nstamp);
+                tc_fence_after();     // no fence.proxy.async: cp.async data is published by the mbarrier it
+                                      // arrives on (same hand-off as CUTLASS' sm100 cp.async mainloop)
                 if (lane == 0) {
-                    const uint32_t a16 = (smem_base + (uint32_t)stage * p.stage_bytes) >> 4;
-                    const uint32_t b16 = a16 + ((uint32_t)p.a_stage_bytes >> 4);
-                    if (!p.b_mn_major) {
-                        // A and B are both K-major with the same contraction bytes: walk sub-tiles
-                        // (128-byte column blocks), 32 bytes (= 2 x 16 B units) per instruction
-                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
-                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
-                            const uint32_t bs = b16 + (uint32_t)sub * b_sub16;
-                            for (int jr = 0; jr < p.q_a; ++jr) {
-                                umma_ss<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
-                                              b_hi | (uint64_t)((bs + 2u * jr) & 0x3FFFu), p.idesc, accumulate);
-                                accumulate = 1u;
-                            }
-                        }
-                    } else {
-                        // dgrad: B is MN-major, one k-step = umma_k rows of the weight box
-                        int j = 0;
-                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
-                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
-                            for (int jr = 0; jr < p.q_a; ++jr, ++j) {
-                                umma_ss<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
-                                              b_hi | (uint64_t)((b16 + (uint32_t)j * p.b_kstep16_mn) & 0x3FFFu),
-                                              p.idesc, accumulate);
-                                accumulate = 1u;
-                            }
+                    if (!(p.debug & 2)) {
+                        const uint4 *dt = desc_tab + stage * 16;
+                        for (int j = 0; j < ksteps; ++j) {
+                            const uint4 d = dt[j];
+                            umma_ss<KIND>(d_tmem, ((uint64_t)d.y << 32) | d.x, ((uint64_t)d.w << 32) | d.z, p.idesc,
+                                          accumulate);
+                            accumulate = 1u;
                         }
                     }
                     tc_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
                 }
                 __syncwarp();
+                TC_STAMP(1, 2 * nstamp + 1);
+                ++nstamp;
                 accumulate = 1u;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
@@ -409,9 +434,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             int64_t dst_row = -1;
             if (my_row < p.rows) dst_row = p.argsort ? (int64_t)__ldg(p.argsort + my_row) : my_row;
             mbar_wait(&tmem_full[acc], acc_phase);
+            if (warp == 0) TC_STAMP(2, 2 * (int)local);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.n);
-            if constexpr (KIND == KIND_F16) {
+            if (p.debug & 4) {
+                // ablation: accumulator is released untouched
+            } else if constexpr (KIND == KIND_F16) {
                 if (p.out_dtype == SPX_F16) epilogue_tile<SPX_F16, false>(p, t_row, dst_row);
                 else epilogue_tile<SPX_BF16, false>(p, t_row, dst_row);
             } else if constexpr (KIND == KIND_TF32) {
@@ -423,13 +451,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 0) TC_STAMP(2, 2 * (int)local + 1);
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 0) TC_STAMP(3, 1);
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
@@ -548,12 +578,16 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.rows = a.rows; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask; p.argsort = a.argsort;
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
+    const char *dbg = getenv("SPX_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    const char *trace = getenv("SPX_TC_TRACE");   // hex device pointer of a [4][2048] int64 buffer
+    p.dbg_ts = trace ? (long long *)strtoull(trace, nullptr, 16) : nullptr;
     return 0;
 }
 
 template <int KIND, int CPR>
 static int launch_tc_cpr(const CUtensorMap &tm, const TcParams &p, cudaStream_t stream) {
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + TC_MAX_STAGES * 16 * 16 /*descriptor table*/;
     static thread_local bool configured = false;
     if (!configured) {
         SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -48,6 +48,17 @@ __device__ __forceinline__ bool group_active(const uint32_t (&tm)[4], int g, con
     return false;
 }
 
+// bit gl set iff group gl of this pass has an active offset in the tile
+__device__ __forceinline__ uint32_t active_groups(const uint32_t (&tm)[4], const uint32_t *gmask, int ng) {
+    uint32_t act = 0;
+    for (int gl = 0; gl < ng; ++gl) {
+        const uint32_t hit = (tm[0] & gmask[gl * 4]) | (tm[1] & gmask[gl * 4 + 1]) | (tm[2] & gmask[gl * 4 + 2]) |
+                             (tm[3] & gmask[gl * 4 + 3]);
+        if (hit) act |= 1u << gl;
+    }
+    return act;
+}
+
 __device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ tile_mask, int64_t tile, int words,
                                                   uint32_t (&out)[4]) {
 #pragma unroll
@@ -82,6 +93,7 @@ tc_wgrad_kernel(const WgParams p) {
     uint64_t *acc_done = bars + 2 * WG_MAX_STAGES + 8;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * WG_MAX_STAGES + 9);
     uint32_t *used_smem = tmem_ptr_smem + 1;
+    uint32_t *gmask = used_smem + 1;                  // [32][4] offsets covered by each group of this pass
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -90,6 +102,19 @@ tc_wgrad_kernel(const WgParams p) {
     const int g_begin = blockIdx.y * p.groups_per_pass;
     const int g_end = min(p.groups_total, g_begin + p.groups_per_pass);
 
+    if (threadIdx.x < 32) {
+        // group gl covers atoms [g*apg, (g+1)*apg) -> kernel offsets a / apo; one thread per group
+        const int g = g_begin + (int)threadIdx.x;
+        uint32_t m[4] = {0, 0, 0, 0};
+        if (g < g_end) {
+            for (int a = g * p.apg; a < (g + 1) * p.apg; ++a) {
+                const int k = a / p.apo;
+                if (k < p.kv) m[k >> 5] |= 1u << (k & 31);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) gmask[threadIdx.x * 4 + w] = m[w];
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], WG_PROD_THREADS); mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) {
@@ -151,9 +176,8 @@ tc_wgrad_kernel(const WgParams p) {
                 if (leader) fetch_indices(next, local + 1);
             }
             mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
-            bool any = false;
-            for (int g = g_begin; g < g_end; ++g) any = any || group_active(tm, g, p);
-            if (any) {
+            const uint32_t act = active_groups(tm, gmask, g_end - g_begin);
+            if (act) {
                 const int32_t *idx_s = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes);
                 // ---- dout tile (MN-major B operand); source rows are block row kv
                 {
@@ -178,8 +202,8 @@ tc_wgrad_kernel(const WgParams p) {
                     ++nb;
                 }
                 // ---- gathered x atoms, one stage per active group
-                for (int g = g_begin; g < g_end; ++g) {
-                    if (!group_active(tm, g, p)) continue;
+                for (uint32_t rem = act; rem; rem &= rem - 1) {
+                    const int g = g_begin + (__ffs(rem) - 1);
                     mbar_wait(&empty_a[stage], phase ^ 1u);
                     const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
                     for (int s = 0; s < p.apg; ++s) {
@@ -222,18 +246,15 @@ tc_wgrad_kernel(const WgParams p) {
             const int64_t next = tile + chunks;
             uint32_t tm_next[4] = {0, 0, 0, 0};
             if (next < num_tiles) wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
-            bool any = false;
-            for (int g = g_begin; g < g_end; ++g) any = any || group_active(tm, g, p);
-            if (any) {
+            const uint32_t act = active_groups(tm, gmask, g_end - g_begin);
+            if (act) {
                 const int bb = (int)(nb & 1);
                 mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
                 const uint32_t b16 = (b_base + (uint32_t)bb * p.b_buf_bytes) >> 4;
-                for (int g = g_begin; g < g_end; ++g) {
-                    if (!group_active(tm, g, p)) continue;
+                for (uint32_t rem = act; rem; rem &= rem - 1) {
+                    const int gl = __ffs(rem) - 1;
                     mbar_wait(&full_a[stage], phase);
                     tc_fence_after();
-                    fence_proxy_async_smem();
-                    const int gl = g - g_begin;
                     if (lane == 0) {
                         const uint32_t a16 = (a_base + (uint32_t)stage * p.a_stage_bytes) >> 4;
                         const uint32_t d_tmem = tmem_base + (uint32_t)(gl * p.n);
@@ -353,7 +374,7 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     if (avail < 2 * p.a_stage_bytes) return false;
     p.stages = avail / p.a_stage_bytes;
     if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
-    pl.smem = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 2 * (size_t)p.idx_bytes + 1024 + 256;
+    pl.smem = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 2 * (size_t)p.idx_bytes + 1024 + 1024;
     int64_t tiles = div_up64(a.n_out, WG_TILE);
     int chunks = sm_count() / pl.passes;
     if (chunks < 1) chunks = 1;

@@ -24,7 +24,8 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // keys per block
 constexpr int RS_FUSED_MAX_BLOCKS = 256;           // above this a scan kernel computes the bases
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int *__restrict__ counts) {
+rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int block_major,
+               int *__restrict__ counts) {
     __shared__ int hist[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) hist[i] = 0;
     __syncthreads();
@@ -35,7 +36,12 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk
         if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (RS_BINS - 1)], 1);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) counts[(int64_t)d * nblk + blockIdx.x] = hist[d];
+    // fused mode: block-major [block][digit] (coalesced here and when every block sums the columns);
+    // scan mode: digit-major [digit][block] (each scan block walks one contiguous row)
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
+        if (block_major) counts[(int64_t)blockIdx.x * RS_BINS + d] = hist[d];
+        else counts[(int64_t)d * nblk + blockIdx.x] = hist[d];
+    }
 }
 
 // large inputs only: counts[d][b] -> exclusive prefix over b, totals[d] = sum_b
@@ -88,9 +94,8 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         const int d = q * RS_THREADS + tid;
         if (FUSED) {
             int tot = 0, before = 0;
-            const int *row = counts + (int64_t)d * nblk;
             for (int b = 0; b < nblk; ++b) {
-                const int c = __ldg(row + b);
+                const int c = __ldg(counts + (int64_t)b * RS_BINS + d);     // coalesced over d
                 tot += c;
                 if (b < blk) before += c;
             }
@@ -191,7 +196,7 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
         int32_t *vout = (pass & 1) ? vals_b : vals_a;
         if (last && pass > 0) { kout = mask; vout = argsort; }      // never aliases kin (kin is a scratch buffer)
         const int shift = pass * RS_BITS;
-        rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, shift, nblk, counts);
+        rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, shift, nblk, fused ? 1 : 0, counts);
         SPX_CHECK_LAUNCH("rs_hist_kernel");
         if (!fused) {
             rs_scan_kernel<<<RS_BINS, RS_THREADS, 0, stream>>>(counts, nblk, totals);

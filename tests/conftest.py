@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the GPU box has >100 host cores: keep torch / BLAS CPU helpers of the tests on a few threads
+    try:
+        import torch
+        torch.set_num_threads(min(8, os.cpu_count() or 1))
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")

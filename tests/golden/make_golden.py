@@ -79,6 +79,9 @@ def main():
         inds.append(np.concatenate([np.full((npts, 1), b, np.int32), cc], 1))
     inds = np.concatenate(inds, 0)
     feats = np.random.uniform(-1, 1, size=(inds.shape[0], C)).astype(np.float32)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import oracle as orc
     out = {}
     for tag, (k, s, p, d) in {"k3s2p1d1": (3, 2, 1, 1), "k3s1p1d1": (3, 1, 1, 1),
                               "k2s2p0d1": (2, 2, 0, 1)}.items():
@@ -89,7 +92,12 @@ def main():
         wt = torch.from_numpy(w).permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
         y = torch.nn.functional.conv3d(dense, wt, stride=s, padding=p, dilation=d)
         dy = torch.from_numpy(np.random.uniform(-0.2, 0.2, size=tuple(y.shape)).astype(np.float32))
-        y.backward(dy)
+        # the sparse op only defines gradients through its ACTIVE outputs: mask dy to them
+        oi, _, _ = orc.get_indice_pairs(inds, bs, shape3, [k] * 3, [s] * 3, [p] * 3, [d] * 3, [0] * 3, False)
+        act = torch.zeros_like(y)
+        act[oi[:, 0], :, oi[:, 1], oi[:, 2], oi[:, 3]] = 1
+        assert float((y.detach() * (1 - act)).abs().max()) == 0.0      # inactive outputs are exactly 0
+        y.backward(dy * act)
         out[f"{tag}_w"] = w
         out[f"{tag}_y"] = y.detach().numpy()
         out[f"{tag}_dy"] = dy.numpy()

@@ -161,24 +161,13 @@ def test_dense_conv_golden(oracle, tag, k, s, p, d):
     assert np.abs(got - y).max() < 1e-4
     dout = dy[out_inds[:, 0], :, out_inds[:, 1], out_inds[:, 2], out_inds[:, 3]]
     din, dwe = oracle.indice_conv_backward(feats, w, dout, pairs, num, False, False)
-    # dense dy is non-zero also where the sparse output has no voxel; those cells feed the dense
-    # gradients but not the sparse ones -> compare on what the sparse op defines:
-    # recompute dense-equivalent with dy masked to the active outputs
-    import torch
-    dense = torch.zeros((2, feats.shape[1], *shape))
-    dense[inds[:, 0], :, inds[:, 1], inds[:, 2], inds[:, 3]] = torch.from_numpy(feats)
-    dense.requires_grad_(True)
-    wt = torch.from_numpy(w).permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
-    yy = torch.nn.functional.conv3d(dense, wt, stride=s, padding=p, dilation=d)
-    mask = torch.zeros_like(yy)
-    mask[out_inds[:, 0], :, out_inds[:, 1], out_inds[:, 2], out_inds[:, 3]] = 1
-    yy.backward(torch.from_numpy(dy) * mask)
-    ref_dw = wt.grad.permute(0, 2, 3, 4, 1).numpy()
-    ref_dx = dense.grad[inds[:, 0], :, inds[:, 1], inds[:, 2], inds[:, 3]].numpy()
-    assert np.abs(dwe - ref_dw).max() < 1e-3
-    assert np.abs(din - ref_dx).max() < 1e-4
-    # every non-active output cell of the dense conv is exactly zero input coverage
-    assert np.abs(y * (1 - mask.numpy())).max() == 0.0
+    # golden gradients: torch dense conv3d backward with dy masked to the active outputs
+    assert np.abs(dwe - dw).max() < 1e-3
+    assert np.abs(din - dx).max() < 1e-4
+    # every non-active output cell of the dense conv is exactly zero
+    active = np.zeros_like(y)
+    active[out_inds[:, 0], :, out_inds[:, 1], out_inds[:, 2], out_inds[:, 3]] = 1
+    assert np.abs(y * (1 - active)).max() == 0.0
 
 
 def test_subm_dense_equivalence(oracle):
