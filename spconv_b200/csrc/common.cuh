@@ -237,6 +237,36 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
     }
 }
 
+// Warp-uniform variants: executed by ALL 32 lanes with identical operands, one elected lane
+// issues.  Keeping the surrounding control flow uniform lets the compiler hold descriptors in
+// uniform registers (no per-MMA R2UR / ELECT retry loop on the single issuing thread).
+template <int KIND>
+__device__ __forceinline__ void umma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    if constexpr (KIND == KIND_F16) {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred pe, pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, pa;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1"); byte quantities, 16-byte granular.
 //   swizzle_bytes in {32, 64, 128}; layout_type: 128B=2, 64B=4, 32B=6
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,

@@ -34,7 +34,7 @@ constexpr int TC_MMA_WARP = 4 + TC_PROD_WARPS;
 constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;
 constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 gather producers | 12 MMA issuer | 13 TMA + index copies
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_CTAS_PER_SM = 1;        // the clock64 timeline shows pipeline DEPTH matters most: one CTA, all smem as stages
+constexpr int TC_CTAS_PER_SM = 2;        // max resident CTAs per SM the kernel is compiled for (SPX_TC_CTAS picks 1 or 2)
 constexpr int TC_SMEM_BUDGET_2 = 104 * 1024;   // per CTA when two CTAs share an SM
 constexpr int TC_SMEM_BUDGET = 200 * 1024;     // per CTA when a tile needs the whole SM
 
@@ -68,7 +68,7 @@ struct TcParams {
     const float *scale, *bias_f32;
     const int8_t *output_add;
     float output_add_scale;
-    long long *dbg_ts;      // optional [4 roles][2048] clock64 stamps of CTA 0 (SPX_TC_TRACE, perf triage)
+    long long *dbg_ts;      // optional [8 roles][2048] clock64 stamps of CTA 0 (SPX_TC_TRACE, perf triage)
     int debug;              // SPX_TC_DEBUG ablation bits (perf triage only): 1 no gather, 2 no MMA, 4 no epilogue, 8 no weight TMA
 };
 
@@ -383,7 +383,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         int64_t tile = blockIdx.x;
         uint32_t tm[4] = {0, 0, 0, 0};
         if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
-        const int ksteps = p.a_subtiles * p.q_a;
+        const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
+        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
+                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
+        const uint32_t b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
         for (; tile < num_tiles; tile += gridDim.x, ++local) {
             const int64_t next = tile + gridDim.x;
             uint32_t tm_next[4] = {0, 0, 0, 0};
@@ -398,19 +401,40 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&full[stage], phase);
                 TC_STAMP(1, 2 * nstamp);
-                tc_fence_after();     // no fence.proxy.async: cp.async data is published by the mbarrier it
+                tc_fence_after();
+                TC_STAMP(4, 2 * nstamp);     // no fence.proxy.async: cp.async data is published by the mbarrier it
                                       // arrives on (same hand-off as CUTLASS' sm100 cp.async mainloop)
-                if (lane == 0) {
-                    if (!(p.debug & 2)) {
-                        const uint4 *dt = desc_tab + stage * 16;
-                        for (int j = 0; j < ksteps; ++j) {
-                            const uint4 d = dt[j];
-                            umma_ss<KIND>(d_tmem, ((uint64_t)d.y << 32) | d.x, ((uint64_t)d.w << 32) | d.z, p.idesc,
-                                          accumulate);
-                            accumulate = 1u;
+                {
+                    // warp-uniform issue: every lane runs the same arithmetic, an elected lane fires
+                    const uint32_t a16 = (smem_base + (uint32_t)stage * p.stage_bytes) >> 4;
+                    const uint32_t b16 = a16 + ((uint32_t)p.a_stage_bytes >> 4);
+                    if (p.debug & 2) {
+                        // ablation: no tensor work
+                    } else if (!p.b_mn_major) {
+                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
+                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
+                            const uint32_t bs = b16 + (uint32_t)sub * b_sub16;
+                            for (int jr = 0; jr < p.q_a; ++jr) {
+                                umma_ss_elect<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
+                                                    b_hi | (uint64_t)((bs + 2u * jr) & 0x3FFFu), p.idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
+                    } else {
+                        int j = 0;
+                        for (int sub = 0; sub < p.a_subtiles; ++sub) {
+                            const uint32_t as = a16 + (uint32_t)sub * (uint32_t)(A_SUB_BYTES >> 4);
+                            for (int jr = 0; jr < p.q_a; ++jr, ++j) {
+                                umma_ss_elect<KIND>(d_tmem, a_hi | (uint64_t)((as + 2u * jr) & 0x3FFFu),
+                                                    b_hi | (uint64_t)((b16 + (uint32_t)j * p.b_kstep16_mn) & 0x3FFFu),
+                                                    p.idesc, accumulate);
+                                accumulate = 1u;
+                            }
                         }
                     }
-                    tc_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
+                    TC_STAMP(4, 2 * nstamp + 1);
+                    tc_commit_elect(&empty[stage]);        // frees the smem stage when these MMAs retire
+                    TC_STAMP(5, 2 * nstamp);
                 }
                 __syncwarp();
                 TC_STAMP(1, 2 * nstamp + 1);
@@ -418,7 +442,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
                 accumulate = 1u;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            if (lane == 0) tc_commit(&tmem_full[acc]);   // accumulator complete
+            tc_commit_elect(&tmem_full[acc]);   // accumulator complete
             __syncwarp();
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
@@ -570,7 +594,9 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     while (cols < (uint32_t)(2 * cy)) cols <<= 1;
     p.tmem_cols = cols;
     // two CTAs per SM when >= 3 pipeline stages and both TMEM allocations fit; else one big CTA
-    p.ctas_per_sm = ((TC_SMEM_BUDGET_2 - 2 * p.idx_bytes) / p.stage_bytes >= 3 && cols <= 256) ? TC_CTAS_PER_SM : 1;
+    const char *ctas_env = getenv("SPX_TC_CTAS");
+    const int want_ctas = ctas_env ? atoi(ctas_env) : 2;
+    p.ctas_per_sm = (want_ctas >= 2 && (TC_SMEM_BUDGET_2 - 2 * p.idx_bytes) / p.stage_bytes >= 3 && cols <= 256) ? 2 : 1;
     const int budget = p.ctas_per_sm == 2 ? TC_SMEM_BUDGET_2 : TC_SMEM_BUDGET;
     p.stages = (budget - 2 * p.idx_bytes) / p.stage_bytes;
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;

@@ -13,6 +13,7 @@
 //     the partials in a fixed order (deterministic; the reference's split-K does the same
 //     with fp32 workspaces, spconv/csrc/sparse/convops.py:1236-1243, :2421-2436).
 #include "gemm.cuh"
+#include <stdlib.h>
 
 namespace spx {
 
@@ -35,6 +36,7 @@ struct WgParams {
     const uint32_t *tile_mask;   // [tiles][words]
     int kv, words, c_in;
     float *partial; int64_t partial_stride;
+    long long *dbg_ts;           // optional [8][2048] clock64 stamps of CTA (0,0) (SPX_TC_TRACE)
 };
 
 __device__ __forceinline__ bool bit_set(const uint32_t (&m)[4], int k) { return (m[k >> 5] >> (k & 31)) & 1u; }
@@ -64,6 +66,8 @@ __device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ t
 #pragma unroll
     for (int w = 0; w < 4; ++w) out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
 }
+
+#define WG_STAMP(role, n) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (n) < 2048) p.dbg_ts[(role) * 2048 + (n)] = clock64(); } while (0)
 
 template <int CPA>     // 16-byte chunks per atom row (= span_x / 16)
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -134,6 +138,7 @@ tc_wgrad_kernel(const WgParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp == 0) WG_STAMP(3, 0);
 
     if (warp >= 4 && warp < WG_MMA_WARP) {
         // ================================================= producers
@@ -142,6 +147,7 @@ tc_wgrad_kernel(const WgParams p) {
         const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;                                  // B buffers filled so far
+        int nst = 0, ntile = 0;
         const int cpr_d = p.db >> 4;                      // 16-byte chunks per dout row
         // per-lane constants of the atom gather: chunk chb of rows r0 + itc*RPI of this warp's 32 rows
         const int r0 = lane >> LG_CPA;
@@ -183,6 +189,7 @@ tc_wgrad_kernel(const WgParams p) {
                 {
                     const int bb = (int)(nb & 1);
                     mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
+                    if (pw == 0) WG_STAMP(6, 2 * ntile);
                     const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
                     const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW;
                     for (int itc = 0; itc * 32 < ROWS_PW * cpr_d; ++itc) {
@@ -199,12 +206,15 @@ tc_wgrad_kernel(const WgParams p) {
                         cp_async_16(dst, src, rsrc >= 0 ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&full_b[bb]);
+                    if (pw == 0) WG_STAMP(6, 2 * ntile + 1);
+                    ++ntile;
                     ++nb;
                 }
                 // ---- gathered x atoms, one stage per active group
                 for (uint32_t rem = act; rem; rem &= rem - 1) {
                     const int g = g_begin + (__ffs(rem) - 1);
                     mbar_wait(&empty_a[stage], phase ^ 1u);
+                    if (pw == 0) WG_STAMP(0, 2 * nst);
                     const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
                     for (int s = 0; s < p.apg; ++s) {
                         const int a = g * p.apg + s;
@@ -222,6 +232,8 @@ tc_wgrad_kernel(const WgParams p) {
                         }
                     }
                     cp_async_mbar_arrive_noinc(&full_a[stage]);
+                    if (pw == 0) WG_STAMP(0, 2 * nst + 1);
+                    ++nst;
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -234,6 +246,7 @@ tc_wgrad_kernel(const WgParams p) {
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;
         uint32_t used = 0;
+        int nst = 0, ntile = 0;
         int64_t tile = chunk;
         uint32_t tm[4] = {0, 0, 0, 0};
         if (tile < num_tiles) wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
@@ -250,36 +263,41 @@ tc_wgrad_kernel(const WgParams p) {
             if (act) {
                 const int bb = (int)(nb & 1);
                 mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
+                WG_STAMP(7, ntile); ++ntile;
                 const uint32_t b16 = (b_base + (uint32_t)bb * p.b_buf_bytes) >> 4;
                 for (uint32_t rem = act; rem; rem &= rem - 1) {
                     const int gl = __ffs(rem) - 1;
                     mbar_wait(&full_a[stage], phase);
+                    WG_STAMP(1, 2 * nst);
                     tc_fence_after();
-                    if (lane == 0) {
+                    {
+                        // warp-uniform issue (see gemm_tc.cu): all lanes compute, an elected lane fires
                         const uint32_t a16 = (a_base + (uint32_t)stage * p.a_stage_bytes) >> 4;
                         const uint32_t d_tmem = tmem_base + (uint32_t)(gl * p.n);
+                        uint32_t acc_flag = (used >> gl) & 1u;
                         for (int j = 0; j < p.ksteps; ++j) {
                             const uint64_t a_desc = a_hi | (uint64_t)((a16 + (uint32_t)j * a_step16) & 0x3FFFu);
                             const uint64_t b_desc = b_hi | (uint64_t)((b16 + (uint32_t)j * b_step16) & 0x3FFFu);
-                            umma_ss<KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, (((used >> gl) & 1u) || j > 0) ? 1u : 0u);
+                            umma_ss_elect<KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, acc_flag);
+                            acc_flag = 1u;
                         }
-                        tc_commit(&empty_a[stage]);
+                        tc_commit_elect(&empty_a[stage]);
                     }
+                    WG_STAMP(1, 2 * nst + 1); ++nst;
                     __syncwarp();
                     used |= 1u << gl;
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                if (lane == 0) tc_commit(&empty_b[bb]);
+                tc_commit_elect(&empty_b[bb]);
                 __syncwarp();
                 ++nb;
             }
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
-        if (lane == 0) {
-            *used_smem = used;
-            tc_commit(acc_done);
-        }
+        if (lane == 0) *used_smem = used;
+        __syncwarp();
+        tc_commit_elect(acc_done);
         __syncwarp();
     } else {
         // ================================================= epilogue: TMEM -> fp32 partials
@@ -316,8 +334,10 @@ tc_wgrad_kernel(const WgParams p) {
         }
     }
 
+    if (warp == 0) WG_STAMP(3, 1);
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) WG_STAMP(3, 2);
     if (warp == WG_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -404,6 +424,10 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     WgPlan pl;
     SPX_REQUIRE(make_plan(a, pl), "tc_wgrad: unsupported shape");
     pl.p.partial = (float *)a.workspace;
+    {
+        const char *trace = getenv("SPX_TC_TRACE");
+        pl.p.dbg_ts = trace ? (long long *)strtoull(trace, nullptr, 16) : nullptr;
+    }
     SPX_REQUIRE((size_t)pl.chunks * pl.p.partial_stride * sizeof(float) <= a.workspace_bytes,
                 "tc_wgrad: workspace too small");
     dim3 grid(pl.chunks, pl.passes);

@@ -21,11 +21,16 @@ def t(fn,n=20):
         flush.zero_(); a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); tot+=a.elapsed_time(b)
     return tot/n*1000
-out={}
-for dbg in [0,1,2,4,8,3,5,6,7,15]:
-    os.environ["SPX_TC_DEBUG"]=str(dbg)
-    f=t(lambda: ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True))
-    out[dbg]=round(f,1)
-os.environ["SPX_TC_DEBUG"]="0"
-bw=t(lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True))
-print(json.dumps({"fwd_us_by_debug":out,"bwd_us":round(bw,1)}))
+res_all={}
+for ctas in ("1","2"):
+    os.environ["SPX_TC_CTAS"]=ctas
+    out={}
+    for dbg in [0,1,2,4,8,15]:
+        os.environ["SPX_TC_DEBUG"]=str(dbg)
+        f=t(lambda: ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True))
+        out[dbg]=round(f,1)
+    os.environ["SPX_TC_DEBUG"]="0"
+    bw=t(lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True))
+    res_all[ctas]={"fwd_us_by_debug":out,"bwd_us":round(bw,1)}
+# host overhead of one op call (empty problem is not possible; time a tiny 128-row problem)
+print(json.dumps(res_all))

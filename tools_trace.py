@@ -13,17 +13,19 @@ x=torch.randn(100000,C,device=dev).half(); w=(torch.randn(K,3,3,3,C,device=dev)*
 res=ops.get_indice_pairs_implicit_gemm(inds,1,shape,ConvAlgo.MaskImplicitGemm,[3]*3,[1]*3,[1]*3,[1]*3,[0]*3,True,False,is_train=True)
 _,_,pf,pb,mf,mb,sf,sb,masks=res
 for _ in range(3): ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True)
-ts=torch.zeros((4,2048),dtype=torch.int64,device=dev)
+ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
 os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
 ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True)
 torch.cuda.synchronize()
 t=ts.cpu().numpy()
 t0=t[3,0]
 def rel(a): return [int(v-t0) for v in a if v>0]
+
 prod=rel(t[0]); mma=rel(t[1]); epi=rel(t[2]); end=int(t[3,1]-t0)
 n=len(prod)//2
 print("kernel cycles (CTA0 role loop start -> final barrier):", end, " stages:", n, " tiles:", len(epi)//2)
-print("stage | prod: got_empty issued | mma: got_full committed")
-for i in range(n):
-    print(f"{i:3d} | {prod[2*i]:7d} {prod[2*i+1]:7d} | {mma[2*i]:7d} {mma[2*i+1]:7d}")
+f4=rel(t[4]); f5=[int(v-t0) for v in t[5][0::2] if v>0]
+print("stage | prod: got_empty issued | mma: got_full fenced mma_issued committed loop_end")
+for i in range(min(n,40)):
+    print(f"{i:3d} | {prod[2*i]:7d} {prod[2*i+1]:7d} | {mma[2*i]:7d} {f4[2*i]:7d} {f4[2*i+1]:7d} {f5[i] if i < len(f5) else -1:7d} {mma[2*i+1]:7d}")
 print("epilogue (start,end):", [(epi[2*i],epi[2*i+1]) for i in range(len(epi)//2)])

@@ -1,0 +1,28 @@
+"""perf triage: clock64 timeline of CTA (0,0) of the weight-gradient kernel (SPX_TC_TRACE)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np, torch
+from bench_utils import surface_cloud
+from spconv_b200.core import ConvAlgo
+from spconv_b200.pytorch import ops
+dev = torch.device("cuda:0")
+shape=[41,1600,1408]; C=K=64
+rng=np.random.default_rng(50051)
+inds=torch.from_numpy(surface_cloud(rng,shape,100000)).to(dev)
+x=torch.randn(100000,C,device=dev).half(); w=(torch.randn(K,3,3,3,C,device=dev)*0.05).half(); dout=torch.randn(100000,K,device=dev).half()
+res=ops.get_indice_pairs_implicit_gemm(inds,1,shape,ConvAlgo.MaskImplicitGemm,[3]*3,[1]*3,[1]*3,[1]*3,[0]*3,True,False,is_train=True)
+_,_,pf,pb,mf,mb,sf,sb,masks=res
+bw=lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True)
+for _ in range(3): bw()
+ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
+os.environ["SPX_TC_DEBUG"]="0"
+os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
+bw(); torch.cuda.synchronize()
+t=ts.cpu().numpy(); t0=t[3,0]
+rel=lambda a:[int(v-t0) for v in a if v>0]
+prod=rel(t[0]); mma=rel(t[1]); pb_=rel(t[6]); mb_=rel(t[7])
+print("loop end / after final sync:", int(t[3,1]-t0), int(t[3,2]-t0), " stages:", len(prod)//2, " tiles:", len(pb_)//2)
+print("tile | prod: got_empty_b issued_b | mma got_full_b")
+for i in range(min(len(pb_)//2,14)): print(f"{i:3d} | {pb_[2*i]:7d} {pb_[2*i+1]:7d} | {mb_[i] if i<len(mb_) else -1:7d}")
+print("stage | prod: got_empty_a issued | mma: got_full_a issued+committed")
+for i in range(min(len(prod)//2,36)): print(f"{i:3d} | {prod[2*i]:7d} {prod[2*i+1]:7d} | {mma[2*i]:7d} {mma[2*i+1]:7d}")
