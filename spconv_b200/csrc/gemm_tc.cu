@@ -220,8 +220,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     uint64_t *idx_full = bars + 2 * TC_MAX_STAGES + 4;    // [2] bulk copy -> producers
     uint64_t *idx_empty = bars + 2 * TC_MAX_STAGES + 6;   // [2] producers -> bulk copy
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 8);
-    // per (stage, k-step) UMMA descriptor pairs, built once: the issuing thread only loads and fires
-    uint4 *desc_tab = reinterpret_cast<uint4 *>(bars + 2 * TC_MAX_STAGES + 10);   // [stages][16]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -236,7 +234,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
             mbar_init(&idx_full[a], 1);      // expect_tx arrival of the bulk copy
-            mbar_init(&idx_empty[a], TC_PROD_THREADS);   // every producer thread releases the buffer
+            mbar_init(&idx_empty[a], TC_PROD_WARPS);     // one release per producer warp
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap_w);
@@ -245,24 +243,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        const int ksteps = p.a_subtiles * p.q_a;
-        const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
-        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
-                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
-        for (int e = lane; e < p.stages * 16; e += 32) {
-            const int st = e >> 4, j = e & 15;
-            if (j < ksteps) {
-                const uint32_t a16 = (smem_base + (uint32_t)st * p.stage_bytes) >> 4;
-                const uint32_t b16 = a16 + ((uint32_t)p.a_stage_bytes >> 4);
-                const uint32_t sub = (uint32_t)(j / p.q_a), jr = (uint32_t)(j % p.q_a);
-                const uint64_t ad = a_hi | (uint64_t)((a16 + sub * (uint32_t)(A_SUB_BYTES >> 4) + 2u * jr) & 0x3FFFu);
-                uint32_t boff;
-                if (!p.b_mn_major) boff = sub * ((uint32_t)p.b_sub_bytes >> 4) + 2u * jr;   // same contraction walk as A
-                else boff = (uint32_t)j * (uint32_t)p.b_kstep16_mn;                         // k-step = UMMA_K weight rows
-                const uint64_t bd = b_hi | (uint64_t)((b16 + boff) & 0x3FFFu);
-                desc_tab[e] = make_uint4((uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32));
-            }
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -300,25 +280,35 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             const int32_t *idx_lane = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes) +
                                       pw * ROWS_PW + r0;
             BitIter it(tm);
-            for (int k = it.next(); k >= 0; k = it.next()) {
+            // the index loads of offset k+1 are issued before the wait on the next free stage
+            int k = it.next();
+            int32_t ridx[ITERS];
+            if (k >= 0) {
+#pragma unroll
+                for (int itc = 0; itc < ITERS; ++itc) ridx[itc] = idx_lane[k * 128 + itc * RPI];
+            }
+            while (k >= 0) {
                 mbar_wait(&empty[stage], phase ^ 1u);
                 if (pw == 0) TC_STAMP(0, 2 * nstamp);
                 const uint32_t a_stage = smem_base + (uint32_t)stage * p.stage_bytes;
-                const int32_t *idx_k = idx_lane + k * 128;
                 if (!(p.debug & 1)) {
 #pragma unroll
-                    for (int itc = 0; itc < ITERS; ++itc) {
-                        const int32_t ridx = idx_k[itc * RPI];
-                        const uint8_t *src = x_lane + (int64_t)max(ridx, 0) * XB;
-                        cp_async_16(a_stage + dst_off[itc], src, ridx >= 0 ? 16u : 0u);
-                    }
+                    for (int itc = 0; itc < ITERS; ++itc)
+                        cp_async_16(a_stage + dst_off[itc], x_lane + (int64_t)max(ridx[itc], 0) * XB,
+                                    ridx[itc] >= 0 ? 16u : 0u);
                 }
                 cp_async_mbar_arrive_noinc(&full[stage]);
                 if (pw == 0) TC_STAMP(0, 2 * nstamp + 1);
                 ++nstamp;
+                k = it.next();
+                if (k >= 0) {
+#pragma unroll
+                    for (int itc = 0; itc < ITERS; ++itc) ridx[itc] = idx_lane[k * 128 + itc * RPI];
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            mbar_arrive(&idx_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&idx_empty[buf]);
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }

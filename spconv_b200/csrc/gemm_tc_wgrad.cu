@@ -51,8 +51,12 @@ __device__ __forceinline__ bool group_active(const uint32_t (&tm)[4], int g, con
 }
 
 // bit gl set iff group gl of this pass has an active offset in the tile
-__device__ __forceinline__ uint32_t active_groups(const uint32_t (&tm)[4], const uint32_t *gmask, int ng) {
+__device__ __forceinline__ uint32_t active_groups(const uint32_t (&tm)[4], const uint32_t *gmask, int ng, int words) {
     uint32_t act = 0;
+    if (words == 1) {                                   // kv <= 32: the common 3x3x3 case
+        for (int gl = 0; gl < ng; ++gl) act |= (tm[0] & gmask[gl * 4]) ? 1u << gl : 0u;
+        return act;
+    }
     for (int gl = 0; gl < ng; ++gl) {
         const uint32_t hit = (tm[0] & gmask[gl * 4]) | (tm[1] & gmask[gl * 4 + 1]) | (tm[2] & gmask[gl * 4 + 2]) |
                              (tm[3] & gmask[gl * 4 + 3]);
@@ -69,15 +73,26 @@ __device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ t
 
 #define WG_STAMP(role, n) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (n) < 2048) p.dbg_ts[(role) * 2048 + (n)] = clock64(); } while (0)
 
-template <int CPA>     // 16-byte chunks per atom row (= span_x / 16)
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&m)[4], int w) {
+    return w == 0 ? m[0] : (w == 1 ? m[1] : (w == 2 ? m[2] : m[3]));     // selects, no local-memory indexing
+}
+
+// CPA = 16-byte chunks per x-atom row (span_x / 16), CPD = 16-byte chunks per dout row (db / 16)
+template <int CPA, int CPD>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgParams p) {
     constexpr int LG_CPA = CPA == 2 ? 1 : (CPA == 4 ? 2 : 3);
     constexpr int RPI = 32 / CPA;
+    constexpr int LG_CPD = CPD == 2 ? 1 : (CPD == 4 ? 2 : (CPD == 8 ? 3 : (CPD == 16 ? 4 : 5)));
+    constexpr int RPI_D = 32 / CPD;                              // dout rows covered by one warp-wide cp.async
+    constexpr int DB = CPD * 16;
+    constexpr int SPAN_D = DB < 128 ? DB : 128;
+    constexpr int LG_SPAN_D = SPAN_D == 128 ? 7 : (SPAN_D == 64 ? 6 : 5);
     constexpr int SPAN_X = CPA * 16;
     constexpr int LG_SPAN_X = LG_CPA + 4;
     constexpr int ROWS_PW = WG_TILE / WG_PROD_WARPS;           // tile rows per producer warp
     constexpr int ITERS = ROWS_PW / RPI > 0 ? ROWS_PW / RPI : 1;   // cp.async per thread per atom
+    constexpr int ITERS_D = ROWS_PW / RPI_D;                       // cp.async per thread per dout tile
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -123,7 +138,7 @@ tc_wgrad_kernel(const WgParams p) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], WG_PROD_THREADS); mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&full_b[b], WG_PROD_THREADS); mbar_init(&empty_b[b], 1);
-            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], WG_PROD_THREADS);
+            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], WG_PROD_WARPS);
         }
         mbar_init(acc_done, 1);
         *used_smem = 0;
@@ -148,7 +163,6 @@ tc_wgrad_kernel(const WgParams p) {
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;                                  // B buffers filled so far
         int nst = 0, ntile = 0;
-        const int cpr_d = p.db >> 4;                      // 16-byte chunks per dout row
         // per-lane constants of the atom gather: chunk chb of rows r0 + itc*RPI of this warp's 32 rows
         const int r0 = lane >> LG_CPA;
         const uint32_t chb = (uint32_t)(lane & (CPA - 1)) << 4;
@@ -158,6 +172,17 @@ tc_wgrad_kernel(const WgParams p) {
         for (int itc = 0; itc < ITERS; ++itc)
             dst_off[itc] = swizzle_offset(((uint32_t)(pw * ROWS_PW + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
         const int lg_apo = p.apo == 1 ? 0 : (p.apo == 2 ? 1 : 2);
+        // per-lane constants of the dout gather: chunk chd of rows rd0 + itc*RPI_D of this warp's rows
+        const int rd0 = lane >> LG_CPD;
+        const uint32_t chd = (uint32_t)(lane & (CPD - 1)) << 4;
+        const uint8_t *d_lane = p.d + chd;
+        uint32_t dstd_off[ITERS_D];
+#pragma unroll
+        for (int itc = 0; itc < ITERS_D; ++itc) {
+            const uint32_t row_in_tile = (uint32_t)(pw * ROWS_PW + rd0 + itc * RPI_D);
+            dstd_off[itc] = (chd >> LG_SPAN_D) * (uint32_t)(WG_TILE * SPAN_D) +
+                            swizzle_offset((row_in_tile << LG_SPAN_D) + (chd & (uint32_t)(SPAN_D - 1)), SPAN_D);
+        }
         auto fetch_indices = [&](int64_t t, int64_t lcl) {
             const int b = (int)(lcl & 1);
             const uint32_t use = (uint32_t)(lcl >> 1);
@@ -177,12 +202,16 @@ tc_wgrad_kernel(const WgParams p) {
             const int buf = (int)(local & 1);
             const int64_t next = tile + chunks;
             uint32_t tm_next[4] = {0, 0, 0, 0};
+            if (pw == 0) WG_STAMP(5, 4 * (int)local);
             if (next < num_tiles) {
                 wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
                 if (leader) fetch_indices(next, local + 1);
             }
+            if (pw == 0) WG_STAMP(5, 4 * (int)local + 1);
             mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
-            const uint32_t act = active_groups(tm, gmask, g_end - g_begin);
+            if (pw == 0) WG_STAMP(5, 4 * (int)local + 2);
+            const uint32_t act = active_groups(tm, gmask, g_end - g_begin, p.words);
+            if (pw == 0) WG_STAMP(5, 4 * (int)local + 3);
             if (act) {
                 const int32_t *idx_s = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes);
                 // ---- dout tile (MN-major B operand); source rows are block row kv
@@ -191,20 +220,14 @@ tc_wgrad_kernel(const WgParams p) {
                     mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
                     if (pw == 0) WG_STAMP(6, 2 * ntile);
                     const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
-                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW;
-                    for (int itc = 0; itc * 32 < ROWS_PW * cpr_d; ++itc) {
-                        const int flat = itc * 32 + lane;
-                        const int r = flat >> p.lg_cpr_d;
-                        const uint32_t byte_in_row = (uint32_t)(flat & (cpr_d - 1)) << 4;
-                        const int32_t rsrc = rows_s[r];
-                        const uint32_t sub = byte_in_row >> p.lg_span_d;
-                        const uint32_t within = byte_in_row & (uint32_t)(p.span_d - 1);
-                        const uint32_t row_in_tile = (uint32_t)(pw * ROWS_PW + r);
-                        const uint32_t dst = dstb + sub * (uint32_t)(WG_TILE * p.span_d) +
-                                             swizzle_offset((row_in_tile << p.lg_span_d) + within, p.span_d);
-                        const uint8_t *src = p.d + (rsrc >= 0 ? (int64_t)rsrc * p.db + byte_in_row : 0);
-                        cp_async_16(dst, src, rsrc >= 0 ? 16u : 0u);
-                    }
+                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW + rd0;
+                    int32_t rsrc[ITERS_D];
+#pragma unroll
+                    for (int itc = 0; itc < ITERS_D; ++itc) rsrc[itc] = rows_s[itc * RPI_D];
+#pragma unroll
+                    for (int itc = 0; itc < ITERS_D; ++itc)
+                        cp_async_16(dstb + dstd_off[itc], d_lane + (int64_t)max(rsrc[itc], 0) * DB,
+                                    rsrc[itc] >= 0 ? 16u : 0u);
                     cp_async_mbar_arrive_noinc(&full_b[bb]);
                     if (pw == 0) WG_STAMP(6, 2 * ntile + 1);
                     ++ntile;
@@ -220,16 +243,17 @@ tc_wgrad_kernel(const WgParams p) {
                         const int a = g * p.apg + s;
                         const int k = a >> lg_apo;
                         const int cb = a & (p.apo - 1);
-                        const bool active = k < p.kv && bit_set(tm, k);
+                        const bool active = k < p.kv && ((pick_word(tm, k >> 5) >> (k & 31)) & 1u);
                         const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * ROWS_PW + r0;
                         const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * SPAN_X);
                         const uint8_t *x_atom = x_lane + cb * SPAN_X;
+                        int32_t ridx[ITERS];                      // all index loads first, then the copies
 #pragma unroll
-                        for (int itc = 0; itc < ITERS; ++itc) {
-                            const int32_t ridx = active ? idx_k[itc * RPI] : -1;
-                            cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx, 0) * p.xb,
-                                        ridx >= 0 ? 16u : 0u);
-                        }
+                        for (int itc = 0; itc < ITERS; ++itc) ridx[itc] = active ? idx_k[itc * RPI] : -1;
+#pragma unroll
+                        for (int itc = 0; itc < ITERS; ++itc)
+                            cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx[itc], 0) * p.xb,
+                                        ridx[itc] >= 0 ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&full_a[stage]);
                     if (pw == 0) WG_STAMP(0, 2 * nst + 1);
@@ -237,7 +261,8 @@ tc_wgrad_kernel(const WgParams p) {
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
-            mbar_arrive(&idx_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&idx_empty[buf]);
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
@@ -252,14 +277,14 @@ tc_wgrad_kernel(const WgParams p) {
         if (tile < num_tiles) wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
         // both operands are MN-major: LBO = distance between 128-row atoms, SBO = 8 rows
         const uint64_t a_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
-        const uint64_t b_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_d), 8u * p.span_d, p.span_d);
+        const uint64_t b_hi = smem_desc_hi((uint32_t)(WG_TILE * SPAN_D), 8u * SPAN_D, SPAN_D);
         const uint32_t a_step16 = (uint32_t)(p.rows_per_kstep * p.span_x) >> 4;
-        const uint32_t b_step16 = (uint32_t)(p.rows_per_kstep * p.span_d) >> 4;
+        const uint32_t b_step16 = (uint32_t)(p.rows_per_kstep * SPAN_D) >> 4;
         for (; tile < num_tiles; tile += chunks) {
             const int64_t next = tile + chunks;
             uint32_t tm_next[4] = {0, 0, 0, 0};
             if (next < num_tiles) wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
-            const uint32_t act = active_groups(tm, gmask, g_end - g_begin);
+            const uint32_t act = active_groups(tm, gmask, g_end - g_begin, p.words);
             if (act) {
                 const int bb = (int)(nb & 1);
                 mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
@@ -344,14 +369,38 @@ tc_wgrad_kernel(const WgParams p) {
     }
 }
 
+// 4 outputs per thread (float4 partial reads), the chunk range split over the 8 warps of a block,
+// partial sums combined through shared memory in warp order (fixed order => deterministic)
+constexpr int RED_WARPS = 8;
 template <typename T>
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int64_t stride, int chunks, int64_t total,
-                                    T *__restrict__ dw) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * stride + i];
-    dw[i] = from_float<T>(s);
+__global__ void __launch_bounds__(RED_WARPS * 32)
+wgrad_reduce_kernel(const float *__restrict__ partial, int64_t stride, int chunks, int64_t total,
+                    T *__restrict__ dw) {
+    __shared__ float4 acc_s[RED_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * 32 + lane) * 4;      // total % 4 == 0 (channels % 16 == 0)
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total) {
+        const int per = (chunks + RED_WARPS - 1) / RED_WARPS;
+        const int c0 = warp * per, c1 = min(chunks, c0 + per);
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(partial + (int64_t)c * stride + i));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    acc_s[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < total) {
+        float4 t = acc_s[0][lane];
+#pragma unroll
+        for (int w = 1; w < RED_WARPS; ++w) {
+            const float4 v = acc_s[w][lane];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        dw[i] = from_float<T>(t.x); dw[i + 1] = from_float<T>(t.y);
+        dw[i + 2] = from_float<T>(t.z); dw[i + 3] = from_float<T>(t.w);
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -430,26 +479,34 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     }
     SPX_REQUIRE((size_t)pl.chunks * pl.p.partial_stride * sizeof(float) <= a.workspace_bytes,
                 "tc_wgrad: workspace too small");
+    SPX_REQUIRE(((uintptr_t)a.workspace & 15u) == 0, "tc_wgrad: workspace must be 16-byte aligned");
     dim3 grid(pl.chunks, pl.passes);
-    static thread_local bool configured[3] = {false, false, false};
-    const int cpa = pl.p.span_x >> 4;
-    const int ci = cpa == 2 ? 0 : (cpa == 4 ? 1 : 2);
-    if (!configured[ci]) {
-        const void *fn = cpa == 2 ? (const void *)tc_wgrad_kernel<2> : cpa == 4 ? (const void *)tc_wgrad_kernel<4>
-                                                                               : (const void *)tc_wgrad_kernel<8>;
-        SPX_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BUDGET + 2048));
-        configured[ci] = true;
+    const int cpa = pl.p.span_x >> 4, cpd = pl.p.db >> 4;
+    using KernelFn = void (*)(const WgParams);
+    KernelFn fn = nullptr;
+#define WG_PICK(A, D) if (cpa == A && cpd == D) fn = tc_wgrad_kernel<A, D>;
+#define WG_PICK_ROW(A) WG_PICK(A, 2) WG_PICK(A, 4) WG_PICK(A, 8) WG_PICK(A, 16) WG_PICK(A, 32)
+    WG_PICK_ROW(2) WG_PICK_ROW(4) WG_PICK_ROW(8)
+#undef WG_PICK_ROW
+#undef WG_PICK
+    SPX_REQUIRE(fn != nullptr, "tc_wgrad: no kernel instance for this channel layout");
+    static thread_local KernelFn configured[16] = {};
+    bool seen = false;
+    for (int i = 0; i < 16; ++i) seen |= configured[i] == fn;
+    if (!seen) {
+        SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            WG_SMEM_BUDGET + 2048));
+        for (int i = 0; i < 16; ++i)
+            if (!configured[i]) { configured[i] = fn; break; }
     }
-    if (cpa == 2) tc_wgrad_kernel<2><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
-    else if (cpa == 4) tc_wgrad_kernel<4><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
-    else tc_wgrad_kernel<8><<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
+    fn<<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
     SPX_CHECK_LAUNCH("tc_wgrad_kernel");
     const int64_t total = pl.p.partial_stride;
-    unsigned nblk = (unsigned)div_up64(total, 256);
+    unsigned nblk = (unsigned)div_up64(total, 128);
     if (a.dtype == SPX_F16)
-        wgrad_reduce_kernel<__half><<<nblk, 256, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__half *)a.dw);
+        wgrad_reduce_kernel<__half><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__half *)a.dw);
     else
-        wgrad_reduce_kernel<__nv_bfloat16><<<nblk, 256, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__nv_bfloat16 *)a.dw);
+        wgrad_reduce_kernel<__nv_bfloat16><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__nv_bfloat16 *)a.dw);
     SPX_CHECK_LAUNCH("wgrad_reduce_kernel");
     return 0;
 }

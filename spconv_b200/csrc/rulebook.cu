@@ -241,37 +241,41 @@ __global__ void subm_probe_kernel(Table table, Geom g, const int32_t *__restrict
 // per-axis range tests, and the nine probes of one z-plane are issued back to back so a thread
 // keeps nine independent 8-byte loads in flight (the generic kernel above exposes one L2 round
 // trip per offset and spends ~150 instructions per probe on generic n-d index arithmetic).
-__global__ void __launch_bounds__(128)
+// One thread per (voxel, z-plane): 3N threads keep the SMs full at N = 1e5 (N threads fill a third
+// of the B200's thread slots) and the three plane masks of a voxel meet in shared memory.
+constexpr int K3_VOX = 128;                    // voxels per block; block = 3 * K3_VOX threads
+__global__ void __launch_bounds__(3 * K3_VOX)
 subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices, int64_t N,
                      int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
                      uint32_t *__restrict__ mask) {
-    const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (o >= N) return;
-    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + o);    // (b, z, y, x)
-    const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
-    const int dz = g.dilation[0], dy = g.dilation[1], dx = g.dilation[2];
-    const bool bok = c.x >= 0 && c.x < g.batch;
-    // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
-    bool vz[3], vy[3], vx[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int qz = c.y + (r - 1) * dz, qy = c.z + (r - 1) * dy, qx = c.w + (r - 1) * dx;
-        vz[r] = bok && qz >= 0 && qz < D0;
-        vy[r] = qy >= 0 && qy < D1;
-        vx[r] = qx >= 0 && qx < D2;
-    }
-    const uint32_t key_c = (uint32_t)(((c.x * D0 + c.y) * D1 + c.z) * D2 + c.w);
-    const int sz = dz * D1 * D2, sy = dy * D2, sx = dx;
+    __shared__ uint32_t plane_mask[3][K3_VOX];
+    const int lo = threadIdx.x % K3_VOX;
+    const int rz = threadIdx.x / K3_VOX;          // warp-uniform (K3_VOX is a multiple of 32)
+    const int64_t o = blockIdx.x * (int64_t)K3_VOX + lo;
     uint32_t mword = 0;
+    if (o < N) {
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + o);    // (b, z, y, x)
+        const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
+        const int dz = g.dilation[0], dy = g.dilation[1], dx = g.dilation[2];
+        // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
+        const int qz = c.y + (rz - 1) * dz;
+        const bool vz = c.x >= 0 && c.x < g.batch && qz >= 0 && qz < D0;
+        bool vy[3], vx[3];
 #pragma unroll
-    for (int rz = 0; rz < 3; ++rz) {
+        for (int r = 0; r < 3; ++r) {
+            const int qy = c.z + (r - 1) * dy, qx = c.w + (r - 1) * dx;
+            vy[r] = qy >= 0 && qy < D1;
+            vx[r] = qx >= 0 && qx < D2;
+        }
+        const int sy = dy * D2, sx = dx;
+        const uint32_t key_p = (uint32_t)(((c.x * D0 + c.y) * D1 + c.z) * D2 + c.w) + (uint32_t)((rz - 1) * dz * D1 * D2);
         unsigned long long slot[9];
         uint32_t key[9], hpos[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             const int ry = j / 3, rx = j % 3;
-            const bool valid = vz[rz] && vy[ry] && vx[rx] && !(rz == 1 && j == 4);
-            key[j] = key_c + (uint32_t)((rz - 1) * sz + (ry - 1) * sy + (rx - 1) * sx);
+            const bool valid = vz && vy[ry] && vx[rx] && !(rz == 1 && j == 4);
+            key[j] = key_p + (uint32_t)((ry - 1) * sy + (rx - 1) * sx);
             hpos[j] = mix32(key[j]) & table.cap_mask;
             slot[j] = valid ? __ldg(&table.slots[hpos[j]]) : Table32::EMPTY;
         }
@@ -284,7 +288,7 @@ subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices,
             } else {
                 unsigned long long cur = slot[j];
                 uint32_t h = hpos[j];
-                while (cur != Table32::EMPTY) {           // collision chain (rare at load factor <= 0.5)
+                while (cur != Table32::EMPTY) {           // collision chain (rare at load factor 0.25)
                     if ((uint32_t)(cur >> 32) == key[j]) { found = (int32_t)(uint32_t)cur; break; }
                     h = (h + 1) & table.cap_mask;
                     cur = __ldg(&table.slots[h]);
@@ -295,7 +299,10 @@ subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices,
             if (found >= 0) mword |= 1u << k;
         }
     }
-    if (mask) mask[o] = mword;
+    if (!mask) return;                                  // uniform over the grid
+    plane_mask[rz][lo] = mword;
+    __syncthreads();
+    if (rz == 0 && o < N) mask[o] = plane_mask[0][lo] | plane_mask[1][lo] | plane_mask[2][lo];
 }
 
 // ------------------------------------------------------------------ regular / transposed conv
@@ -534,31 +541,40 @@ __global__ void gather_rows_kernel(const uint32_t *__restrict__ src, const int32
 
 // ------------------------------------------------------------------ tile-blocked gather table
 // one block per 128-row tile; see include/spconv_b200.h (spx_build_tile_table)
-__global__ void __launch_bounds__(128)
+constexpr int TT_SPLIT = 4;                     // threads per tile row: offsets k = q, q + 4, ...
+__global__ void __launch_bounds__(128 * TT_SPLIT)
 build_tile_table_kernel(const int32_t *__restrict__ pair, int64_t pair_stride, int kv,
                         const int32_t *__restrict__ argsort, const uint32_t *__restrict__ mask, int64_t rows,
                         int words, int32_t *__restrict__ table, uint32_t *__restrict__ tile_mask) {
     const int64_t t = blockIdx.x;
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127;
+    const int q = threadIdx.x >> 7;             // warp-uniform
     const int64_t j = t * 128 + r;
     int32_t src = -1;
     if (j < rows) src = argsort ? __ldg(argsort + j) : (int32_t)j;
     int32_t *blk = table + t * (int64_t)(kv + 1) * 128;
-    for (int k = 0; k < kv; ++k)
-        blk[k * 128 + r] = src >= 0 ? __ldg(pair + (int64_t)k * pair_stride + src) : -1;
-    blk[kv * 128 + r] = src;
+    // 3N x 4 threads with <= 8 independent scattered 4-byte loads each: the kernel is a pure
+    // L2-latency problem, so it is sized for memory-level parallelism, not for work per thread
+    const int32_t *col = pair + (src >= 0 ? src : 0);
+#pragma unroll 8
+    for (int k = q; k < kv; k += TT_SPLIT)
+        blk[k * 128 + r] = src >= 0 ? __ldg(col + (int64_t)k * pair_stride) : -1;
+    if (q == 0) blk[kv * 128 + r] = src;
     __shared__ uint32_t red[4][4];
-    for (int w = 0; w < words; ++w) {
-        uint32_t m = 0;
-        if (j < rows) {
-            if (mask) m = __ldg(mask + j * words + w);
-            else { int hi = kv - 32 * w; m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u); }
+    if (q == 0) {
+        for (int w = 0; w < words; ++w) {
+            uint32_t m = 0;
+            if (j < rows) {
+                if (mask) m = __ldg(mask + j * words + w);
+                else { int hi = kv - 32 * w; m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u); }
+            }
+            m = __reduce_or_sync(0xffffffffu, m);
+            if ((r & 31) == 0) red[w][r >> 5] = m;
         }
-        m = __reduce_or_sync(0xffffffffu, m);
-        if ((r & 31) == 0) red[w][r >> 5] = m;
     }
     __syncthreads();
-    if (r < words) tile_mask[t * words + r] = red[r][0] | red[r][1] | red[r][2] | red[r][3];
+    if (threadIdx.x < words) tile_mask[t * words + threadIdx.x] = red[threadIdx.x][0] | red[threadIdx.x][1] |
+                                                                  red[threadIdx.x][2] | red[threadIdx.x][3];
 }
 
 }  // namespace spx
@@ -656,7 +672,8 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
         subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("subm_insert_kernel");
         if (gg.ndim == 3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3) {
-            subm_probe_k3_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask);
+            subm_probe_k3_kernel<<<(unsigned)div_up64(N, K3_VOX), 3 * K3_VOX, 0, stream>>>(t, gg, indices, N, pair_fwd,
+                                                                                           pair_bwd, mask);
         } else {
             subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
         }
@@ -917,7 +934,7 @@ extern "C" int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, in
     SPX_REQUIRE(pair && table && tile_mask, "build_tile_table: NULL pointer argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     int words = (kv + 31) / 32;
-    build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128, 0, stream>>>(pair, pair_stride, kv, argsort, mask,
+    build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128 * TT_SPLIT, 0, stream>>>(pair, pair_stride, kv, argsort, mask,
                                                                              rows, words, table, tile_mask);
     SPX_CHECK_LAUNCH("build_tile_table_kernel");
     return 0;

@@ -4,11 +4,14 @@
 // (spconv/csrc/sparse/all.py:935-1000).  For the rulebook sizes of this path (1e5..1e6 keys) a
 // library radix sort is launch/latency-bound: CUB's onesweep spends ~12 us per 8-bit pass plus
 // histogram/scan kernels (~80 us for 100 k keys, measured on B200).  This version uses 9-bit
-// digits (3 passes for the 27-bit masks of a 3x3x3 kernel instead of 4), two small kernels per
-// pass, and nothing else:
-//   hist    : per-block digit histogram -> counts[digit][block]
-//   scatter : every block derives its global digit bases from `counts` (no separate scan kernel
-//             for <= 256 blocks), ranks its keys stably with warp match_any, and scatters.
+// digits (3 passes for the 27-bit masks of a 3x3x3 kernel instead of 4) and two small kernels per
+// pass:
+//   hist    : (first pass only) per-block digit histogram -> counts[digit][block]
+//   scan    : one block per digit: exclusive prefix over blocks + digit totals; also clears the
+//             histogram buffer of the NEXT pass
+//   scatter : ranks its keys stably with warp match_any, scatters them, and accumulates the next
+//             pass's per-block histogram with global atomics keyed by the destination block
+//             (destination positions are known here, so no later pass re-reads keys to count).
 // The first pass reads the masks with an implicit iota payload, the last pass writes the sorted
 // masks back in place (thrust semantics) and the argsort.
 #include "common.cuh"
@@ -21,11 +24,11 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 4;                        // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // keys per block
-constexpr int RS_FUSED_MAX_BLOCKS = 256;           // above this a scan kernel computes the bases
+constexpr int RS_TILE_SHIFT = 10;
+static_assert((1 << RS_TILE_SHIFT) == RS_TILE, "tile shift");
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int block_major,
-               int *__restrict__ counts) {
+rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int *__restrict__ counts) {
     __shared__ int hist[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) hist[i] = 0;
     __syncthreads();
@@ -36,18 +39,16 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk
         if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (RS_BINS - 1)], 1);
     }
     __syncthreads();
-    // fused mode: block-major [block][digit] (coalesced here and when every block sums the columns);
-    // scan mode: digit-major [digit][block] (each scan block walks one contiguous row)
-    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
-        if (block_major) counts[(int64_t)blockIdx.x * RS_BINS + d] = hist[d];
-        else counts[(int64_t)d * nblk + blockIdx.x] = hist[d];
-    }
+    // digit-major [digit][block]: each scan block walks one contiguous row
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) counts[(int64_t)d * nblk + blockIdx.x] = hist[d];
 }
 
-// large inputs only: counts[d][b] -> exclusive prefix over b, totals[d] = sum_b
+// counts[d][b] -> exclusive prefix over b, totals[d] = sum_b; zeroes row d of the next pass's buffer
 __global__ void __launch_bounds__(RS_THREADS)
-rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals) {
+rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals, int *__restrict__ clear_next) {
     const int d = blockIdx.x;
+    if (clear_next)
+        for (int b = threadIdx.x; b < nblk; b += RS_THREADS) clear_next[(int64_t)d * nblk + b] = 0;
     __shared__ int warp_sums[RS_WARPS];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -75,12 +76,12 @@ rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals) {
     if (threadIdx.x == 0) totals[d] = carry_s;
 }
 
-// FUSED: bases are summed from raw counts by every block; else counts already hold block prefixes
-template <bool FUSED, bool IOTA_IN>
+// counts hold block prefixes (rs_scan_kernel); counts_next (may be null) receives the next pass's histogram
+template <bool IOTA_IN>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
                   int nblk, const int *__restrict__ counts, const int *__restrict__ totals,
-                  uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
+                  uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out, int *__restrict__ counts_next) {
     __shared__ int digit_base[RS_BINS];             // global position of this block's first key of each digit
     __shared__ int warp_cnt[RS_WARPS][RS_BINS];     // running per-warp digit counts -> warp bases
     __shared__ int scan_tmp[RS_WARPS];
@@ -92,18 +93,8 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
 #pragma unroll
     for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
         const int d = q * RS_THREADS + tid;
-        if (FUSED) {
-            int tot = 0, before = 0;
-            for (int b = 0; b < nblk; ++b) {
-                const int c = __ldg(counts + (int64_t)b * RS_BINS + d);     // coalesced over d
-                tot += c;
-                if (b < blk) before += c;
-            }
-            my_total[q] = tot; my_before[q] = before;
-        } else {
-            my_total[q] = __ldg(totals + d);
-            my_before[q] = __ldg(counts + (int64_t)d * nblk + blk);
-        }
+        my_total[q] = __ldg(totals + d);
+        my_before[q] = __ldg(counts + (int64_t)d * nblk + blk);
     }
     for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
     // exclusive scan of the 512 digit totals (digit d = q*256 + tid; q-major order keeps d ascending)
@@ -153,22 +144,31 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         for (int w = 0; w < RS_WARPS; ++w) { const int c = warp_cnt[w][d]; warp_cnt[w][d] = acc; acc += c; }
     }
     __syncthreads();
-    // ---- (4) scatter
+    // ---- (4) scatter (+ next pass's histogram, keyed by the destination block; keys that share
+    //      (next digit, destination block) inside a warp are counted by one atomic)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const int64_t i = tile_base + r * 32 + lane;
-        if (i < n) {
+        const bool ok = i < n;
+        int pos = 0;
+        if (ok) {
             const int d = (int)((key[r] >> shift) & (RS_BINS - 1));
-            const int pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
+            pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
+        }
+        if (counts_next) {
+            const int dn = (int)((key[r] >> (shift + RS_BITS)) & (RS_BINS - 1));
+            const int cell = ok ? dn * nblk + (pos >> RS_TILE_SHIFT) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, cell);
+            if (ok && lane == __ffs(peers) - 1) atomicAdd(counts_next + cell, __popc(peers));
         }
     }
 }
 
 size_t radix_argsort_workspace_bytes(int64_t n) {
     const int64_t nblk = div_up64(n > 0 ? n : 1, RS_TILE);
-    return 4 * align_up((size_t)n * 4, 256) + align_up((size_t)RS_BINS * nblk * 4, 256) + align_up(RS_BINS * 4, 256) + 1024;
+    return 4 * align_up((size_t)n * 4, 256) + 2 * align_up((size_t)RS_BINS * nblk * 4, 256) + align_up(RS_BINS * 4, 256) + 1024;
 }
 
 // keys: mask [n] (sorted in place on return), argsort [n] out.  Returns 0 / error code.
@@ -181,34 +181,30 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
     uint32_t *keys_b = ws.take<uint32_t>(n);
     int32_t *vals_b = ws.take<int32_t>(n);
     const int nblk = (int)div_up64(n, RS_TILE);
-    int *counts = ws.take<int>((size_t)RS_BINS * nblk);
+    int *counts_ab[2] = {ws.take<int>((size_t)RS_BINS * nblk), ws.take<int>((size_t)RS_BINS * nblk)};
     int *totals = ws.take<int>(RS_BINS);
     SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 32) key_bits = 32;
     const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
-    const bool fused = nblk <= RS_FUSED_MAX_BLOCKS;
     const uint32_t *kin = mask;
     const int32_t *vin = nullptr;
+    rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, 0, nblk, counts_ab[0]);
+    SPX_CHECK_LAUNCH("rs_hist_kernel");
     for (int pass = 0; pass < passes; ++pass) {
         const bool last = pass == passes - 1;
         uint32_t *kout = (pass & 1) ? keys_b : keys_a;
         int32_t *vout = (pass & 1) ? vals_b : vals_a;
         if (last && pass > 0) { kout = mask; vout = argsort; }      // never aliases kin (kin is a scratch buffer)
         const int shift = pass * RS_BITS;
-        rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, shift, nblk, fused ? 1 : 0, counts);
-        SPX_CHECK_LAUNCH("rs_hist_kernel");
-        if (!fused) {
-            rs_scan_kernel<<<RS_BINS, RS_THREADS, 0, stream>>>(counts, nblk, totals);
-            SPX_CHECK_LAUNCH("rs_scan_kernel");
-        }
-        if (pass == 0) {
-            if (fused) rs_scatter_kernel<true, true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
-            else rs_scatter_kernel<false, true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
-        } else {
-            if (fused) rs_scatter_kernel<true, false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
-            else rs_scatter_kernel<false, false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout);
-        }
+        int *counts = counts_ab[pass & 1];
+        int *counts_next = last ? nullptr : counts_ab[(pass + 1) & 1];
+        rs_scan_kernel<<<RS_BINS, RS_THREADS, 0, stream>>>(counts, nblk, totals, counts_next);
+        SPX_CHECK_LAUNCH("rs_scan_kernel");
+        if (pass == 0)
+            rs_scatter_kernel<true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout, counts_next);
+        else
+            rs_scatter_kernel<false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout, counts_next);
         SPX_CHECK_LAUNCH("rs_scatter_kernel");
         kin = kout; vin = vout;
     }

@@ -1,6 +1,6 @@
 """perf triage: time fwd / dgrad / wgrad kernels of the bench workload under SPX_TC_DEBUG ablations"""
 import os, sys, json, subprocess
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from bench_utils import surface_cloud
 import spconv_b200.pytorch as spconv

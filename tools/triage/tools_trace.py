@@ -1,6 +1,6 @@
 """perf triage: per-stage clock64 timeline of CTA 0 of the forward kernel (SPX_TC_TRACE)"""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from bench_utils import surface_cloud
 from spconv_b200.core import ConvAlgo

@@ -1,6 +1,6 @@
 """perf triage: clock64 timeline of CTA (0,0) of the weight-gradient kernel (SPX_TC_TRACE)"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from bench_utils import surface_cloud
 from spconv_b200.core import ConvAlgo
@@ -24,5 +24,8 @@ prod=rel(t[0]); mma=rel(t[1]); pb_=rel(t[6]); mb_=rel(t[7])
 print("loop end / after final sync:", int(t[3,1]-t0), int(t[3,2]-t0), " stages:", len(prod)//2, " tiles:", len(pb_)//2)
 print("tile | prod: got_empty_b issued_b | mma got_full_b")
 for i in range(min(len(pb_)//2,14)): print(f"{i:3d} | {pb_[2*i]:7d} {pb_[2*i+1]:7d} | {mb_[i] if i<len(mb_) else -1:7d}")
+t5=rel(t[5])
+print("tile top | after fetch | after idx_full | after active_groups")
+for i in range(min(len(t5)//4,14)): print(i, t5[4*i:4*i+4])
 print("stage | prod: got_empty_a issued | mma: got_full_a issued+committed")
 for i in range(min(len(prod)//2,36)): print(f"{i:3d} | {prod[2*i]:7d} {prod[2*i+1]:7d} | {mma[2*i]:7d} {mma[2*i+1]:7d}")
