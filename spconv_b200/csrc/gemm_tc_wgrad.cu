@@ -41,13 +41,15 @@ struct WgParams {
 
 __device__ __forceinline__ bool bit_set(const uint32_t (&m)[4], int k) { return (m[k >> 5] >> (k & 31)) & 1u; }
 
-// offsets covered by group g: atoms [g*apg, (g+1)*apg) -> offsets a / apo
-__device__ __forceinline__ bool group_active(const uint32_t (&tm)[4], int g, const WgParams &p) {
-    const int a0 = g * p.apg, a1 = a0 + p.apg;
-    int k0 = a0 / p.apo, k1 = (a1 - 1) / p.apo;
-    for (int k = k0; k <= k1 && k < p.kv; ++k)
-        if (bit_set(tm, k)) return true;
-    return false;
+// Offset slots are filled in the order 0, kv-1, 1, kv-2, ...: a group (one M = 128 accumulator)
+// then stacks an offset with its point mirror.  On surface-like clouds a voxel that has the
+// neighbour +d usually has -d too, so the two halves of a group are active together and almost no
+// all-zero atom is gathered (with the natural order k, k+1 about half of the gathered atoms of
+// config 2 were zero fill).  Any permutation is valid; this one only changes which TMEM rows an
+// offset owns.
+__device__ __forceinline__ int slot_offset(int slot, int kv) {
+    if (slot >= kv) return kv;                       // padding slot of the last group
+    return (slot & 1) ? kv - 1 - (slot >> 1) : (slot >> 1);
 }
 
 // bit gl set iff group gl of this pass has an active offset in the tile
@@ -122,12 +124,12 @@ tc_wgrad_kernel(const WgParams p) {
     const int g_end = min(p.groups_total, g_begin + p.groups_per_pass);
 
     if (threadIdx.x < 32) {
-        // group gl covers atoms [g*apg, (g+1)*apg) -> kernel offsets a / apo; one thread per group
+        // group gl covers atoms [g*apg, (g+1)*apg) -> offset slots a / apo; one thread per group
         const int g = g_begin + (int)threadIdx.x;
         uint32_t m[4] = {0, 0, 0, 0};
         if (g < g_end) {
             for (int a = g * p.apg; a < (g + 1) * p.apg; ++a) {
-                const int k = a / p.apo;
+                const int k = slot_offset(a / p.apo, p.kv);
                 if (k < p.kv) m[k >> 5] |= 1u << (k & 31);
             }
         }
@@ -191,80 +193,94 @@ tc_wgrad_kernel(const WgParams p) {
             bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
                           p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
         };
+        // dout tile (MN-major B operand) of the tile whose index block is idx_s; source rows = block row kv
+        auto issue_b = [&](const int32_t *idx_s) {
+            const int bb = (int)(nb & 1);
+            mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
+            if (pw == 0) WG_STAMP(6, 2 * ntile);
+            const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
+            const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW + rd0;
+            int32_t rsrc[ITERS_D];
+#pragma unroll
+            for (int itc = 0; itc < ITERS_D; ++itc) rsrc[itc] = rows_s[itc * RPI_D];
+#pragma unroll
+            for (int itc = 0; itc < ITERS_D; ++itc)
+                cp_async_16(dstb + dstd_off[itc], d_lane + (int64_t)max(rsrc[itc], 0) * DB, rsrc[itc] >= 0 ? 16u : 0u);
+            cp_async_mbar_arrive_noinc(&full_b[bb]);
+            if (pw == 0) WG_STAMP(6, 2 * ntile + 1);
+            ++ntile;
+            ++nb;
+        };
+        auto idx_block = [&](int b) {
+            return reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)b * p.idx_bytes);
+        };
+        // Software pipeline over tiles: while the x atoms of tile t are being gathered, the index
+        // block of tile t+1 is already in flight, and right after the first stage of tile t its
+        // group set is computed and its dout tile is issued -- nothing but the first x stage sits
+        // on the tile boundary.
         int64_t local = 0;
         int64_t tile = chunk;
         uint32_t tm[4] = {0, 0, 0, 0};
+        uint32_t act = 0;
         if (tile < num_tiles) {
             if (leader) fetch_indices(tile, 0);
             wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
+            mbar_wait(&idx_full[0], 0u);
+            act = active_groups(tm, gmask, g_end - g_begin, p.words);
+            if (act) issue_b(idx_block(0));
         }
         for (; tile < num_tiles; tile += chunks, ++local) {
             const int buf = (int)(local & 1);
             const int64_t next = tile + chunks;
+            const bool has_next = next < num_tiles;
             uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (pw == 0) WG_STAMP(5, 4 * (int)local);
-            if (next < num_tiles) {
+            if (has_next) {
                 wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
                 if (leader) fetch_indices(next, local + 1);
             }
-            if (pw == 0) WG_STAMP(5, 4 * (int)local + 1);
-            mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
-            if (pw == 0) WG_STAMP(5, 4 * (int)local + 2);
-            const uint32_t act = active_groups(tm, gmask, g_end - g_begin, p.words);
-            if (pw == 0) WG_STAMP(5, 4 * (int)local + 3);
-            if (act) {
-                const int32_t *idx_s = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes);
-                // ---- dout tile (MN-major B operand); source rows are block row kv
-                {
-                    const int bb = (int)(nb & 1);
-                    mbar_wait(&empty_b[bb], (uint32_t)(((nb >> 1) & 1) ^ 1));
-                    if (pw == 0) WG_STAMP(6, 2 * ntile);
-                    const uint32_t dstb = b_base + (uint32_t)bb * p.b_buf_bytes;
-                    const int32_t *rows_s = idx_s + p.kv * 128 + pw * ROWS_PW + rd0;
-                    int32_t rsrc[ITERS_D];
+            uint32_t act_next = 0;
+            bool next_ready = !has_next;
+            auto prepare_next = [&]() {
+                mbar_wait(&idx_full[buf ^ 1], (uint32_t)(((local + 1) >> 1) & 1));
+                act_next = active_groups(tm_next, gmask, g_end - g_begin, p.words);
+                if (act_next) issue_b(idx_block(buf ^ 1));
+                next_ready = true;
+            };
+            const int32_t *idx_s = idx_block(buf);
+            // ---- gathered x atoms, one stage per active group
+            for (uint32_t rem = act; rem; rem &= rem - 1) {
+                const int g = g_begin + (__ffs(rem) - 1);
+                mbar_wait(&empty_a[stage], phase ^ 1u);
+                if (pw == 0) WG_STAMP(0, 2 * nst);
+                const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
+                for (int s = 0; s < p.apg; ++s) {
+                    const int a = g * p.apg + s;
+                    const int k = slot_offset(a >> lg_apo, p.kv);
+                    const int cb = a & (p.apo - 1);
+                    const bool active = k < p.kv && ((pick_word(tm, k >> 5) >> (k & 31)) & 1u);
+                    const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * ROWS_PW + r0;
+                    const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * SPAN_X);
+                    const uint8_t *x_atom = x_lane + cb * SPAN_X;
+                    int32_t ridx[ITERS];                      // all index loads first, then the copies
 #pragma unroll
-                    for (int itc = 0; itc < ITERS_D; ++itc) rsrc[itc] = rows_s[itc * RPI_D];
+                    for (int itc = 0; itc < ITERS; ++itc) ridx[itc] = active ? idx_k[itc * RPI] : -1;
 #pragma unroll
-                    for (int itc = 0; itc < ITERS_D; ++itc)
-                        cp_async_16(dstb + dstd_off[itc], d_lane + (int64_t)max(rsrc[itc], 0) * DB,
-                                    rsrc[itc] >= 0 ? 16u : 0u);
-                    cp_async_mbar_arrive_noinc(&full_b[bb]);
-                    if (pw == 0) WG_STAMP(6, 2 * ntile + 1);
-                    ++ntile;
-                    ++nb;
+                    for (int itc = 0; itc < ITERS; ++itc)
+                        cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx[itc], 0) * p.xb,
+                                    ridx[itc] >= 0 ? 16u : 0u);
                 }
-                // ---- gathered x atoms, one stage per active group
-                for (uint32_t rem = act; rem; rem &= rem - 1) {
-                    const int g = g_begin + (__ffs(rem) - 1);
-                    mbar_wait(&empty_a[stage], phase ^ 1u);
-                    if (pw == 0) WG_STAMP(0, 2 * nst);
-                    const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
-                    for (int s = 0; s < p.apg; ++s) {
-                        const int a = g * p.apg + s;
-                        const int k = a >> lg_apo;
-                        const int cb = a & (p.apo - 1);
-                        const bool active = k < p.kv && ((pick_word(tm, k >> 5) >> (k & 31)) & 1u);
-                        const int32_t *idx_k = idx_s + (active ? k : 0) * 128 + pw * ROWS_PW + r0;
-                        const uint32_t atom_base = a_stage + (uint32_t)s * (uint32_t)(WG_TILE * SPAN_X);
-                        const uint8_t *x_atom = x_lane + cb * SPAN_X;
-                        int32_t ridx[ITERS];                      // all index loads first, then the copies
-#pragma unroll
-                        for (int itc = 0; itc < ITERS; ++itc) ridx[itc] = active ? idx_k[itc * RPI] : -1;
-#pragma unroll
-                        for (int itc = 0; itc < ITERS; ++itc)
-                            cp_async_16(atom_base + dst_off[itc], x_atom + (int64_t)max(ridx[itc], 0) * p.xb,
-                                        ridx[itc] >= 0 ? 16u : 0u);
-                    }
-                    cp_async_mbar_arrive_noinc(&full_a[stage]);
-                    if (pw == 0) WG_STAMP(0, 2 * nst + 1);
-                    ++nst;
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                }
+                cp_async_mbar_arrive_noinc(&full_a[stage]);
+                if (pw == 0) WG_STAMP(0, 2 * nst + 1);
+                ++nst;
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (!next_ready) prepare_next();
             }
+            if (!next_ready) prepare_next();
             __syncwarp();
             if (lane == 0) mbar_arrive(&idx_empty[buf]);
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
+            act = act_next;
         }
     } else if (warp == WG_MMA_WARP) {
         // ================================================= MMA issuer
@@ -336,8 +352,9 @@ tc_wgrad_kernel(const WgParams p) {
         for (int g = g_begin; g < g_end; ++g) {
             const int gl = g - g_begin;
             const int a = g * p.apg + s;
-            const int k = a / p.apo;
-            const int c = (a - k * p.apo) * p.atom_elems + ce;
+            const int ks = a / p.apo;
+            const int k = slot_offset(ks, p.kv);
+            const int c = (a - ks * p.apo) * p.atom_elems + ce;
             const bool valid = k < p.kv;
             const bool has = (used >> gl) & 1u;
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(gl * p.n);

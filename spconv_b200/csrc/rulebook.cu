@@ -279,21 +279,30 @@ subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices,
             hpos[j] = mix32(key[j]) & table.cap_mask;
             slot[j] = valid ? __ldg(&table.slots[hpos[j]]) : Table32::EMPTY;
         }
+        // collision chains advance in ROUNDS: every unresolved probe of the thread steps to its next
+        // slot in the same round, so a warp pays max-chain-length L2 round trips, not their sum
+        uint32_t pending = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            if (slot[j] != Table32::EMPTY && (uint32_t)(slot[j] >> 32) != key[j]) pending |= 1u << j;
+        while (pending) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                if (pending & (1u << j)) {
+                    hpos[j] = (hpos[j] + 1) & table.cap_mask;
+                    slot[j] = __ldg(&table.slots[hpos[j]]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if ((pending & (1u << j)) && (slot[j] == Table32::EMPTY || (uint32_t)(slot[j] >> 32) == key[j]))
+                    pending &= ~(1u << j);
+        }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             const int k = rz * 9 + j;
-            int32_t found = -1;
-            if (k == 13) {
-                found = (int32_t)o;                       // centre: identity
-            } else {
-                unsigned long long cur = slot[j];
-                uint32_t h = hpos[j];
-                while (cur != Table32::EMPTY) {           // collision chain (rare at load factor 0.25)
-                    if ((uint32_t)(cur >> 32) == key[j]) { found = (int32_t)(uint32_t)cur; break; }
-                    h = (h + 1) & table.cap_mask;
-                    cur = __ldg(&table.slots[h]);
-                }
-            }
+            int32_t found = slot[j] != Table32::EMPTY ? (int32_t)(uint32_t)slot[j] : -1;
+            if (k == 13) found = (int32_t)o;              // centre: identity
             pair_fwd[(int64_t)k * N + o] = found;
             if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
             if (found >= 0) mword |= 1u << k;

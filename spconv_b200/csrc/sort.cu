@@ -10,8 +10,9 @@
 //   scan    : one block per digit: exclusive prefix over blocks + digit totals; also clears the
 //             histogram buffer of the NEXT pass
 //   scatter : ranks its keys stably with warp match_any, scatters them, and accumulates the next
-//             pass's per-block histogram with global atomics keyed by the destination block
-//             (destination positions are known here, so no later pass re-reads keys to count).
+//             pass's per-block histogram keyed by the destination block (destination positions are
+//             known here, so no later pass re-reads keys to count): merged per block in shared
+//             memory, then one global atomic per distinct (digit, block) cell.
 // The first pass reads the masks with an implicit iota payload, the last pass writes the sorted
 // masks back in place (thrust semantics) and the argsort.
 #include "common.cuh"
@@ -24,6 +25,8 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 4;                        // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // keys per block
+constexpr int RS_AGG_BITS = 11;
+constexpr int RS_AGG_SLOTS = 1 << RS_AGG_BITS;     // shared-memory merge table, 2x the keys of a block
 constexpr int RS_TILE_SHIFT = 10;
 static_assert((1 << RS_TILE_SHIFT) == RS_TILE, "tile shift");
 
@@ -85,8 +88,10 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     __shared__ int digit_base[RS_BINS];             // global position of this block's first key of each digit
     __shared__ int warp_cnt[RS_WARPS][RS_BINS];     // running per-warp digit counts -> warp bases
     __shared__ int scan_tmp[RS_WARPS];
+    __shared__ int agg_cell[RS_AGG_SLOTS], agg_cnt[RS_AGG_SLOTS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int blk = blockIdx.x;
+    for (int i = tid; i < RS_AGG_SLOTS; i += RS_THREADS) { agg_cell[i] = -1; agg_cnt[i] = 0; }
 
     // ---- (1) per-digit: total over all blocks and the part before this block
     int my_total[RS_BINS / RS_THREADS], my_before[RS_BINS / RS_THREADS];
@@ -144,25 +149,35 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         for (int w = 0; w < RS_WARPS; ++w) { const int c = warp_cnt[w][d]; warp_cnt[w][d] = acc; acc += c; }
     }
     __syncthreads();
-    // ---- (4) scatter (+ next pass's histogram, keyed by the destination block; keys that share
-    //      (next digit, destination block) inside a warp are counted by one atomic)
+    // ---- (4) scatter (+ next pass's histogram, keyed by the destination block).  The cells
+    //      (next digit, destination block) hit by one block are few when either digit is skewed
+    //      (3x3x3 masks: the dz = +-1 planes are mostly empty), and all blocks would hammer the
+    //      same handful of global counters; they are first merged in a small shared-memory
+    //      open-addressing table and flushed with one global atomic per distinct cell.
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const int64_t i = tile_base + r * 32 + lane;
-        const bool ok = i < n;
-        int pos = 0;
-        if (ok) {
+        if (i < n) {
             const int d = (int)((key[r] >> shift) & (RS_BINS - 1));
-            pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
+            const int pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
+            if (counts_next) {
+                const int dn = (int)((key[r] >> (shift + RS_BITS)) & (RS_BINS - 1));
+                const int cell = dn * nblk + (pos >> RS_TILE_SHIFT);
+                uint32_t slot = ((uint32_t)cell * 2654435761u) >> (32 - RS_AGG_BITS);
+                while (true) {
+                    const int prev = atomicCAS(&agg_cell[slot], -1, cell);
+                    if (prev == -1 || prev == cell) { atomicAdd(&agg_cnt[slot], 1); break; }
+                    slot = (slot + 1) & (RS_AGG_SLOTS - 1);        // <= 1024 cells in 2048 slots: terminates
+                }
+            }
         }
-        if (counts_next) {
-            const int dn = (int)((key[r] >> (shift + RS_BITS)) & (RS_BINS - 1));
-            const int cell = ok ? dn * nblk + (pos >> RS_TILE_SHIFT) : -1;
-            const unsigned peers = __match_any_sync(0xffffffffu, cell);
-            if (ok && lane == __ffs(peers) - 1) atomicAdd(counts_next + cell, __popc(peers));
-        }
+    }
+    if (counts_next) {
+        __syncthreads();
+        for (int s2 = tid; s2 < RS_AGG_SLOTS; s2 += RS_THREADS)
+            if (agg_cell[s2] >= 0) atomicAdd(counts_next + agg_cell[s2], agg_cnt[s2]);
     }
 }
 
