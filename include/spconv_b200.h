@@ -90,8 +90,17 @@ int64_t spx_conv_max_out(const spx_conv_geometry *g, int64_t num_in);
  * `words` = ceil(kv/32).
  */
 int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
-                      int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask,
+                      int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask, int32_t *row_table,
                       void *workspace, size_t workspace_bytes, spx_stream_t stream);
+
+/*
+ * Optional by-product of spx_subm_rulebook: row_table [N][32] int32 (16-byte aligned), row o =
+ * pair_fwd[0..kv-1][o] padded with -1 -- the forward table transposed to one 128-byte line per
+ * voxel.  spx_build_tile_table re-reads the rulebook in mask_argsort order; from this copy that
+ * costs 4 sectors per row instead of one per (row, offset).  Produced only for geometries where
+ * this returns 1 (3-D 3x3x3 with 32-bit keys); pass NULL otherwise.
+ */
+int spx_subm_row_table_supported(const spx_conv_geometry *g);
 
 /*
  * Regular / transposed conv rulebook, two-phase because the output count M is
@@ -169,11 +178,24 @@ typedef struct {
  *             (spconv/csrc/sparse/convops.py:2180-2189)
  * tiles = ceil(rows / 128).  Built once per rulebook, shared by fwd / dgrad / wgrad of every
  * layer that shares the indice_key.
+ *
+ * The `table` buffer (spx_tile_table_elems int32 elements, 16-byte aligned) continues behind the
+ * blocks with what the dynamically scheduled kernels need:
+ *   records [tiles][8] int32: {tile, mask words[4], 0, 0, 0}, tiles in order of decreasing
+ *             offset count (ties: ascending tile) -- fwd / dgrad CTAs draw tickets from an atomic
+ *             counter and take tiles in this order (longest-processing-time-first scheduling);
+ *   scratch [64] int32: ticket counter + finished-CTA counter.  Zero after the build and after
+ *             every launch (the last CTA resets it); consequently ONE launch at a time may use a
+ *             given table (launches on the same stream are fine, concurrent streams are not).
  */
 size_t spx_tile_table_elems(int64_t rows, int kv);
+/*
+ * row_table (optional, kv <= 32): the [rows][32] by-product of spx_subm_rulebook for the same
+ * `pair`; when given, `pair` is not read.
+ */
 int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, int kv, const int32_t *argsort,
-                         const uint32_t *mask, int64_t rows, int32_t *table, uint32_t *tile_mask,
-                         spx_stream_t stream);
+                         const uint32_t *mask, int64_t rows, const int32_t *row_table,
+                         int32_t *table, uint32_t *tile_mask, spx_stream_t stream);
 
 /*
  * out[o, :] = act( sum_k x[pair[k][o], :] @ W[:, k, :]^T  + bias )      rows = n_out

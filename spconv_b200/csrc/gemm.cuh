@@ -44,6 +44,18 @@ struct WgradArgs {
     size_t workspace_bytes;
 };
 
+// Layout of the buffer spx_build_tile_table fills (int32 elements):
+//   [tiles][kv+1][128]              gather blocks
+//   [tiles][TT_REC_INTS]            schedule records {tile, mask[4], 0, 0, 0}, heaviest tile first
+//   [TT_STATE_INTS]                 scheduler scratch: [0] ticket counter, [1] finished CTAs
+//                                   (zero between launches; a launch leaves it zero again)
+constexpr int TT_REC_INTS = 8;
+constexpr int TT_STATE_INTS = 64;
+__host__ __device__ inline int64_t tt_blocks_elems(int64_t tiles, int kv) { return tiles * (int64_t)(kv + 1) * 128; }
+__host__ __device__ inline int64_t tt_total_elems(int64_t tiles, int kv) {
+    return tt_blocks_elems(tiles, kv) + tiles * TT_REC_INTS + TT_STATE_INTS;
+}
+
 int simt_gather_gemm(const GatherGemmArgs &a, cudaStream_t stream);
 int simt_wgrad(const WgradArgs &a, cudaStream_t stream);
 

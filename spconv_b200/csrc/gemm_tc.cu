@@ -32,7 +32,10 @@ constexpr int TC_PROD_WARPS = 8;         // 16 tile rows per producer warp
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_MMA_WARP = 4 + TC_PROD_WARPS;
 constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;
-constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 gather producers | 12 MMA issuer | 13 TMA + index copies
+constexpr int TC_SCHED_WARP = TC_TMA_WARP + 1;
+constexpr int TC_THREADS = (TC_SCHED_WARP + 1) * 32;  // warps 0-3 epilogue | 4-11 gather producers | 12 MMA issuer | 13 weight TMA | 14 tile scheduler + index copies
+constexpr int TC_INFO_DEPTH = 4;         // tile-info ring (scheduler -> every role)
+constexpr int TC_INFO_READERS = TC_PROD_WARPS + 1 + 1 + 4;   // producer warps, MMA warp, TMA warp, epilogue warps
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_CTAS_PER_SM = 2;        // max resident CTAs per SM the kernel is compiled for (SPX_TC_CTAS picks 1 or 2)
 constexpr int TC_SMEM_BUDGET_2 = 104 * 1024;   // per CTA when two CTAs share an SM
@@ -56,7 +59,8 @@ struct TcParams {
     // rows
     int64_t rows;
     const int32_t *tile_table;   // [tiles][kv+1][128]
-    const uint32_t *tile_mask;   // [tiles][words]
+    const int32_t *sched_rec;    // [tiles][TT_REC_INTS] schedule records, heaviest tile first (gemm.cuh)
+    int *sched_state;            // [0] ticket counter, [1] finished CTAs; zero between launches
     const int32_t *argsort;      // destination rows of the epilogue (NULL = identity)
     int kv, words, reverse;
     // epilogue
@@ -84,18 +88,6 @@ struct BitIter {
         return -1;
     }
 };
-
-// per-tile offset set (warp-uniform); an all-zero mask still runs offset 0 (all rows "-1" -> zeros)
-__device__ __forceinline__ void load_tile_mask(const uint32_t *__restrict__ tile_mask, int64_t tile, int words,
-                                               uint32_t (&out)[4]) {
-    uint32_t any = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
-        any |= out[w];
-    }
-    if (!any) out[0] = 1u;
-}
 
 // ------------------------------------------------------------------ epilogue, one row per thread
 // 16 accumulator columns -> OUT type, 16-byte vector stores.  OUT is an spx_dtype code.
@@ -189,6 +181,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t t_row,
     }
 }
 
+// per-CTA wall-clock spans (ns, %globaltimer): rows 6..7 of the trace buffer hold [cta][4] =
+// {kernel entry, prologue done, role loops done, exit}
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_SPAN(i) do { if (p.dbg_ts && threadIdx.x == 0 && blockIdx.x < 1024) p.dbg_ts[6 * 2048 + blockIdx.x * 4 + (i)] = global_ns(); } while (0)
 #define TC_STAMP(role, n) do { if (p.dbg_ts && blockIdx.x == 0 && lane == 0 && (n) < 2048) p.dbg_ts[(role) * 2048 + (n)] = clock64(); } while (0)
 
 template <int KIND, int CPR>
@@ -205,6 +205,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     static_assert(ROWS_PW * CPR >= 32, "a producer warp must cover at least one full cp.async instruction");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    TC_SPAN(0);
     // dynamic smem base is only guaranteed 16-byte aligned: align manually to 1024
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -219,11 +220,29 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     uint64_t *tmem_empty = bars + 2 * TC_MAX_STAGES + 2;  // [2] epilogue -> MMA
     uint64_t *idx_full = bars + 2 * TC_MAX_STAGES + 4;    // [2] bulk copy -> producers
     uint64_t *idx_empty = bars + 2 * TC_MAX_STAGES + 6;   // [2] producers -> bulk copy
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 8);
+    uint64_t *info_full = bars + 2 * TC_MAX_STAGES + 8;                    // [TC_INFO_DEPTH] scheduler -> roles
+    uint64_t *info_empty = bars + 2 * TC_MAX_STAGES + 8 + TC_INFO_DEPTH;   // [TC_INFO_DEPTH] roles -> scheduler
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 8 + 2 * TC_INFO_DEPTH);
+    int32_t *info = reinterpret_cast<int32_t *>(tmem_ptr_smem + 2);        // [TC_INFO_DEPTH][8]: {tile, mask[4]}
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t num_tiles = (p.rows + TC_TILE_M - 1) / TC_TILE_M;
+
+    // Tiles are handed out dynamically: the scheduler warp draws a ticket, looks the tile and its
+    // offset set up in the schedule records (heaviest first => LPT list scheduling) and publishes
+    // them through the info ring; every other role consumes ring entries in order.  Entry n uses
+    // ring slot n % TC_INFO_DEPTH and index buffer n % 2; tile < 0 ends the stream.
+    auto read_info = [&](int n, uint32_t (&tm)[4]) -> int {
+        const int e = n & (TC_INFO_DEPTH - 1);
+        mbar_wait(&info_full[e], (uint32_t)((n / TC_INFO_DEPTH) & 1));
+        const volatile int32_t *r = info + e * 8;
+        const int tile = r[0];
+        tm[0] = (uint32_t)r[1]; tm[1] = (uint32_t)r[2]; tm[2] = (uint32_t)r[3]; tm[3] = (uint32_t)r[4];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&info_empty[e]);
+        return tile;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -235,6 +254,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
             mbar_init(&idx_full[a], 1);      // expect_tx arrival of the bulk copy
             mbar_init(&idx_empty[a], TC_PROD_WARPS);     // one release per producer warp
+        }
+        for (int e = 0; e < TC_INFO_DEPTH; ++e) {
+            mbar_init(&info_full[e], 1);
+            mbar_init(&info_empty[e], TC_INFO_READERS);  // one release per reading warp
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap_w);
@@ -249,6 +272,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (warp == 0) TC_STAMP(3, 0);
+    TC_SPAN(1);
 
     if (warp >= 4 && warp < TC_MMA_WARP) {
         // ================================================= gather producers
@@ -267,16 +291,11 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         }
         int stage = 0; uint32_t phase = 0;
         int nstamp = 0;
-        int64_t local = 0;
-        int64_t tile = blockIdx.x;
-        uint32_t tm[4] = {0, 0, 0, 0};
-        if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
-        for (; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int buf = (int)(local & 1);
-            const int64_t next = tile + gridDim.x;
-            uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (next < num_tiles) load_tile_mask(p.tile_mask, next, p.words, tm_next);
-            mbar_wait(&idx_full[buf], (uint32_t)((local >> 1) & 1));
+        for (int n = 0;; ++n) {
+            uint32_t tm[4];
+            if (read_info(n, tm) < 0) break;
+            const int buf = n & 1;
+            mbar_wait(&idx_full[buf], (uint32_t)((n >> 1) & 1));
             const int32_t *idx_lane = reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)buf * p.idx_bytes) +
                                       pw * ROWS_PW + r0;
             BitIter it(tm);
@@ -309,41 +328,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&idx_empty[buf]);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
     } else if (warp == TC_TMA_WARP) {
-        // ================================================= TMA warp: weight boxes + gather-index blocks
+        // ================================================= TMA warp: one weight box per (tile, offset) stage
         // all 32 lanes walk the loops together (the CTA-wide barrier at the end must be reached
         // convergently); lane 0 issues the copies
-        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
-        // the gather-index block of tile t+1 is bulk-copied while tile t is being gathered
-        auto fetch_indices = [&](int64_t t, int64_t lcl) {
-            const int b = (int)(lcl & 1);
-            const uint32_t use = (uint32_t)(lcl >> 1);
-            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
-                bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
-                              p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
-            }
-            __syncwarp();
-        };
         int stage = 0; uint32_t phase = 0;
-        int64_t local = 0;
-        int64_t tile = blockIdx.x;
-        uint32_t tm[4] = {0, 0, 0, 0};
-        if (tile < num_tiles) {
-            fetch_indices(tile, 0);
-            load_tile_mask(p.tile_mask, tile, p.words, tm);
-        }
-        for (; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int64_t next = tile + gridDim.x;
-            uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (next < num_tiles) {
-                load_tile_mask(p.tile_mask, next, p.words, tm_next);
-                fetch_indices(next, local + 1);
-            }
+        for (int n = 0;; ++n) {
+            uint32_t tm[4];
+            if (read_info(n, tm) < 0) break;
             BitIter it(tm);
             for (int k = it.next(); k >= 0; k = it.next()) {
                 mbar_wait(&empty[stage], phase ^ 1u);
@@ -362,25 +355,60 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-#pragma unroll
-            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
+    } else if (warp == TC_SCHED_WARP) {
+        // ================================================= tile scheduler + gather-index blocks
+        // A free index buffer is the permission to look ONE tile ahead: the ticket for entry n is
+        // drawn only when the buffer of entry n-2 has been released, so a CTA never hoards tiles
+        // and the tail of the kernel is at most one (light) tile long.
+        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
+        for (int n = 0;; ++n) {
+            const int b = n & 1, e = n & (TC_INFO_DEPTH - 1);
+            mbar_wait(&idx_empty[b], (uint32_t)(((n >> 1) & 1) ^ 1));
+            mbar_wait(&info_empty[e], (uint32_t)(((n / TC_INFO_DEPTH) & 1) ^ 1));
+            int tile = -1;
+            if (lane == 0) {
+                const int ticket = atomicAdd(p.sched_state, 1);
+                int4 r0 = make_int4(-1, 1, 0, 0), r1 = make_int4(0, 0, 0, 0);
+                if ((int64_t)ticket < num_tiles) {
+                    const int4 *rp = reinterpret_cast<const int4 *>(p.sched_rec + (int64_t)ticket * TT_REC_INTS);
+                    r0 = __ldg(rp); r1 = __ldg(rp + 1);
+                }
+                tile = r0.x;
+                int32_t *dst = info + e * 8;
+                dst[0] = r0.x; dst[1] = r0.y; dst[2] = r0.z; dst[3] = r0.w; dst[4] = r1.x;
+                if (tile >= 0) {
+                    mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
+                    bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
+                                  p.tile_table + (int64_t)tile * (p.kv + 1) * 128, blk_bytes, &idx_full[b]);
+                }
+                mbar_arrive(&info_full[e]);          // release: publishes the record written above
+            }
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < 0) break;
+        }
+        // the last CTA to run dry leaves the scheduler state zeroed for the next launch
+        if (lane == 0) {
+            __threadfence();
+            const int done = atomicAdd(p.sched_state + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.sched_state[0] = 0;
+                p.sched_state[1] = 0;
+                __threadfence();
+            }
+        }
+        __syncwarp();
     } else if (warp == TC_MMA_WARP) {
         // ================================================= MMA issuer
         int nstamp = 0;
         int stage = 0; uint32_t phase = 0;
-        int64_t local = 0;
-        int64_t tile = blockIdx.x;
-        uint32_t tm[4] = {0, 0, 0, 0};
-        if (tile < num_tiles) load_tile_mask(p.tile_mask, tile, p.words, tm);
         const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
         const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
                                            : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
         const uint32_t b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
-        for (; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int64_t next = tile + gridDim.x;
-            uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (next < num_tiles) load_tile_mask(p.tile_mask, next, p.words, tm_next);
+        for (int local = 0;; ++local) {
+            uint32_t tm[4];
+            if (read_info(local, tm) < 0) break;
             const int acc = (int)(local & 1);
             const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -434,14 +462,14 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
             }
             tc_commit_elect(&tmem_full[acc]);   // accumulator complete
             __syncwarp();
-#pragma unroll
-            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
         }
     } else {
         // ================================================= epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31)
-        int64_t local = 0;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int64_t base = tile * TC_TILE_M;
+        for (int local = 0;; ++local) {
+            uint32_t tm_unused[4];
+            const int tile = read_info(local, tm_unused);
+            if (tile < 0) break;
+            const int64_t base = (int64_t)tile * TC_TILE_M;
             const int acc = (int)(local & 1);
             const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
             const int64_t my_row = base + warp * 32 + lane;
@@ -473,10 +501,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
     tc_fence_before();
     __syncthreads();
     if (warp == 0) TC_STAMP(3, 1);
+    TC_SPAN(2);
     if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
+    TC_SPAN(3);
 }
 
 // ------------------------------------------------------------------ host side
@@ -591,7 +621,13 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.stages = (budget - 2 * p.idx_bytes) / p.stage_bytes;
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
     SPX_REQUIRE(p.stages >= 2, "tc_gather_gemm: tile does not fit shared memory (stage %d bytes)", p.stage_bytes);
-    p.rows = a.rows; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask; p.argsort = a.argsort;
+    p.rows = a.rows; p.tile_table = a.tile_table; p.argsort = a.argsort;
+    {
+        const int64_t tiles = div_up64(a.rows, TC_TILE_M);
+        p.sched_rec = a.tile_table + tt_blocks_elems(tiles, a.kv);
+        // scheduler scratch lives in the caller's tile-table buffer (include/spconv_b200.h)
+        p.sched_state = const_cast<int *>(reinterpret_cast<const int *>(p.sched_rec + tiles * TT_REC_INTS));
+    }
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
     const char *dbg = getenv("SPX_TC_DEBUG");
@@ -603,7 +639,7 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
 
 template <int KIND, int CPR>
 static int launch_tc_cpr(const CUtensorMap &tm, const TcParams &p, cudaStream_t stream) {
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + TC_MAX_STAGES * 16 * 16 /*descriptor table*/;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 1024 /*barriers, tile-info ring*/;
     static thread_local bool configured = false;
     if (!configured) {
         SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,

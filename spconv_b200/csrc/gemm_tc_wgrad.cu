@@ -23,14 +23,16 @@ constexpr int WG_PROD_THREADS = WG_PROD_WARPS * 32;
 constexpr int WG_MMA_WARP = 4 + WG_PROD_WARPS;
 constexpr int WG_THREADS = (WG_MMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 producers | 12 MMA issuer
 constexpr int WG_MAX_STAGES = 6;
-constexpr int WG_SMEM_BUDGET = 200 * 1024;
+constexpr int WG_SMEM_BUDGET = 200 * 1024;    // operand stages are sized inside this ...
+constexpr int WG_SMEM_MAX = 224 * 1024;       // ... what is left up to here buys deeper index prefetch
+constexpr int WG_MAX_IDX = 4;                 // index-block ring depth (prefetch distance = depth - 1 tiles)
 
 struct WgParams {
     const uint8_t *x; int xb, span_x, lg_span_x, apo, apg, atom_elems;
     const uint8_t *d; int db, span_d, lg_span_d, lg_cpr_d;
     int n; uint32_t idesc; int ksteps, rows_per_kstep;
     int groups_total, groups_per_pass;
-    int stages, a_stage_bytes, b_buf_bytes, idx_bytes;
+    int stages, a_stage_bytes, b_buf_bytes, idx_bytes, idx_bufs;
     int64_t rows;
     const int32_t *tile_table;   // [tiles][kv+1][128]
     const uint32_t *tile_mask;   // [tiles][words]
@@ -100,19 +102,19 @@ tc_wgrad_kernel(const WgParams p) {
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t *smem = smem_raw + pad;
     const uint32_t smem_base = raw_addr + pad;
-    // layout: [2 x B buffer][stages x A stage][2 x index block][barriers]
+    // layout: [2 x B buffer][stages x A stage][idx_bufs x index block][barriers]
     const uint32_t b_base = smem_base;
     const uint32_t a_base = smem_base + 2u * p.b_buf_bytes;
     const uint32_t idx_off = 2u * p.b_buf_bytes + (uint32_t)p.stages * p.a_stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + idx_off + 2u * p.idx_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + idx_off + (uint32_t)p.idx_bufs * p.idx_bytes);
     uint64_t *full_a = bars;                          // [stages]
     uint64_t *empty_a = bars + WG_MAX_STAGES;         // [stages]
     uint64_t *full_b = bars + 2 * WG_MAX_STAGES;      // [2]
     uint64_t *empty_b = bars + 2 * WG_MAX_STAGES + 2; // [2]
-    uint64_t *idx_full = bars + 2 * WG_MAX_STAGES + 4;  // [2]
-    uint64_t *idx_empty = bars + 2 * WG_MAX_STAGES + 6; // [2]
-    uint64_t *acc_done = bars + 2 * WG_MAX_STAGES + 8;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * WG_MAX_STAGES + 9);
+    uint64_t *idx_full = bars + 2 * WG_MAX_STAGES + 4;                // [WG_MAX_IDX]
+    uint64_t *idx_empty = bars + 2 * WG_MAX_STAGES + 4 + WG_MAX_IDX;  // [WG_MAX_IDX]
+    uint64_t *acc_done = bars + 2 * WG_MAX_STAGES + 4 + 2 * WG_MAX_IDX;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(acc_done + 1);
     uint32_t *used_smem = tmem_ptr_smem + 1;
     uint32_t *gmask = used_smem + 1;                  // [32][4] offsets covered by each group of this pass
 
@@ -138,10 +140,8 @@ tc_wgrad_kernel(const WgParams p) {
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_a[s], WG_PROD_THREADS); mbar_init(&empty_a[s], 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&full_b[b], WG_PROD_THREADS); mbar_init(&empty_b[b], 1);
-            mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], WG_PROD_WARPS);
-        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&full_b[b], WG_PROD_THREADS); mbar_init(&empty_b[b], 1); }
+        for (int b = 0; b < p.idx_bufs; ++b) { mbar_init(&idx_full[b], 1); mbar_init(&idx_empty[b], WG_PROD_WARPS); }
         mbar_init(acc_done, 1);
         *used_smem = 0;
         mbar_fence_init();
@@ -185,13 +185,13 @@ tc_wgrad_kernel(const WgParams p) {
             dstd_off[itc] = (chd >> LG_SPAN_D) * (uint32_t)(WG_TILE * SPAN_D) +
                             swizzle_offset((row_in_tile << LG_SPAN_D) + (chd & (uint32_t)(SPAN_D - 1)), SPAN_D);
         }
-        auto fetch_indices = [&](int64_t t, int64_t lcl) {
-            const int b = (int)(lcl & 1);
-            const uint32_t use = (uint32_t)(lcl >> 1);
-            mbar_wait(&idx_empty[b], (use & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&idx_full[b], blk_bytes);
-            bulk_copy_g2s(smem_base + idx_off + (uint32_t)b * p.idx_bytes,
-                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[b]);
+        // index-block ring: slot / use count advance together with the tile counters (no modulo)
+        const int nring = p.idx_bufs;
+        auto fetch_indices = [&](int64_t t, int slot, uint32_t use) {
+            mbar_wait(&idx_empty[slot], (use & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&idx_full[slot], blk_bytes);
+            bulk_copy_g2s(smem_base + idx_off + (uint32_t)slot * p.idx_bytes,
+                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[slot]);
         };
         // dout tile (MN-major B operand) of the tile whose index block is idx_s; source rows = block row kv
         auto issue_b = [&](const int32_t *idx_s) {
@@ -218,35 +218,45 @@ tc_wgrad_kernel(const WgParams p) {
         // block of tile t+1 is already in flight, and right after the first stage of tile t its
         // group set is computed and its dout tile is issued -- nothing but the first x stage sits
         // on the tile boundary.
-        int64_t local = 0;
         int64_t tile = chunk;
-        uint32_t tm[4] = {0, 0, 0, 0};
+        int cur_slot = 0; uint32_t cur_use = 0;          // ring position of the tile being gathered
+        int pf_slot = 0; uint32_t pf_use = 0;            // ring position of the next block to fetch
+        int64_t pf_tile = chunk;
+        auto prefetch_one = [&]() {                      // leader only
+            if (pf_tile < num_tiles) {
+                fetch_indices(pf_tile, pf_slot, pf_use);
+                pf_tile += chunks;
+                if (++pf_slot == nring) { pf_slot = 0; ++pf_use; }
+            }
+        };
+        uint32_t tm[4] = {0, 0, 0, 0}, tm1[4] = {0, 0, 0, 0};
         uint32_t act = 0;
         if (tile < num_tiles) {
-            if (leader) fetch_indices(tile, 0);
+            if (leader)
+                for (int i = 0; i < nring - 1; ++i) prefetch_one();
             wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
+            if (tile + chunks < num_tiles) wg_load_tile_mask(p.tile_mask, tile + chunks, p.words, tm1);
             mbar_wait(&idx_full[0], 0u);
             act = active_groups(tm, gmask, g_end - g_begin, p.words);
             if (act) issue_b(idx_block(0));
         }
-        for (; tile < num_tiles; tile += chunks, ++local) {
-            const int buf = (int)(local & 1);
+        for (; tile < num_tiles; tile += chunks) {
             const int64_t next = tile + chunks;
             const bool has_next = next < num_tiles;
-            uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (has_next) {
-                wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
-                if (leader) fetch_indices(next, local + 1);
-            }
+            uint32_t tm2[4] = {0, 0, 0, 0};              // tile masks run two tiles ahead
+            if (next + chunks < num_tiles) wg_load_tile_mask(p.tile_mask, next + chunks, p.words, tm2);
+            if (leader) prefetch_one();                  // block of tile + (nb-1)
+            int nxt_slot = cur_slot + 1; uint32_t nxt_use = cur_use;
+            if (nxt_slot == nring) { nxt_slot = 0; ++nxt_use; }
             uint32_t act_next = 0;
             bool next_ready = !has_next;
             auto prepare_next = [&]() {
-                mbar_wait(&idx_full[buf ^ 1], (uint32_t)(((local + 1) >> 1) & 1));
-                act_next = active_groups(tm_next, gmask, g_end - g_begin, p.words);
-                if (act_next) issue_b(idx_block(buf ^ 1));
+                mbar_wait(&idx_full[nxt_slot], nxt_use & 1u);
+                act_next = active_groups(tm1, gmask, g_end - g_begin, p.words);
+                if (act_next) issue_b(idx_block(nxt_slot));
                 next_ready = true;
             };
-            const int32_t *idx_s = idx_block(buf);
+            const int32_t *idx_s = idx_block(cur_slot);
             // ---- gathered x atoms, one stage per active group
             for (uint32_t rem = act; rem; rem &= rem - 1) {
                 const int g = g_begin + (__ffs(rem) - 1);
@@ -277,10 +287,11 @@ tc_wgrad_kernel(const WgParams p) {
             }
             if (!next_ready) prepare_next();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&idx_empty[buf]);
+            if (lane == 0) mbar_arrive(&idx_empty[cur_slot]);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) tm[w] = tm_next[w];
+            for (int w = 0; w < 4; ++w) { tm[w] = tm1[w]; tm1[w] = tm2[w]; }
             act = act_next;
+            cur_slot = nxt_slot; cur_use = nxt_use;
         }
     } else if (warp == WG_MMA_WARP) {
         // ================================================= MMA issuer
@@ -460,7 +471,10 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     if (avail < 2 * p.a_stage_bytes) return false;
     p.stages = avail / p.a_stage_bytes;
     if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
-    pl.smem = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 2 * (size_t)p.idx_bytes + 1024 + 1024;
+    size_t fixed = 2 * (size_t)p.b_buf_bytes + (size_t)p.stages * p.a_stage_bytes + 1024 + 1024;
+    p.idx_bufs = 2;
+    while (p.idx_bufs < WG_MAX_IDX && fixed + (size_t)(p.idx_bufs + 1) * p.idx_bytes <= (size_t)WG_SMEM_MAX) ++p.idx_bufs;
+    pl.smem = fixed + (size_t)p.idx_bufs * p.idx_bytes;
     int64_t tiles = div_up64(a.n_out, WG_TILE);
     int chunks = sm_count() / pl.passes;
     if (chunks < 1) chunks = 1;
@@ -512,7 +526,7 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     for (int i = 0; i < 16; ++i) seen |= configured[i] == fn;
     if (!seen) {
         SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            WG_SMEM_BUDGET + 2048));
+                                            WG_SMEM_MAX));
         for (int i = 0; i < 16; ++i)
             if (!configured[i]) { configured[i] = fn; break; }
     }

@@ -11,6 +11,7 @@
 //     offset-major order (atomicMin of k*N+i, then a radix sort of the minima), compact
 //     "Native" pairs come from a stable per-offset scan instead of atomicAggInc.
 #include "common.cuh"
+#include "gemm.cuh"
 #include <cub/cub.cuh>
 
 namespace spx {
@@ -237,81 +238,68 @@ __global__ void subm_probe_kernel(Table table, Geom g, const int32_t *__restrict
 }
 
 // 3-D, 3x3x3 (any dilation), 32-bit keys -- the shape of every SubMConv3d in SECOND-style nets.
-// The neighbour key is the centre key plus a per-offset constant, validity is a product of three
-// per-axis range tests, and the nine probes of one z-plane are issued back to back so a thread
-// keeps nine independent 8-byte loads in flight (the generic kernel above exposes one L2 round
-// trip per offset and spends ~150 instructions per probe on generic n-d index arithmetic).
-// One thread per (voxel, z-plane): 3N threads keep the SMs full at N = 1e5 (N threads fill a third
-// of the B200's thread slots) and the three plane masks of a voxel meet in shared memory.
-constexpr int K3_VOX = 128;                    // voxels per block; block = 3 * K3_VOX threads
-__global__ void __launch_bounds__(3 * K3_VOX)
+// (The generic kernel above exposes one L2 round trip per offset and spends ~150 instructions per
+// probe on generic n-d index arithmetic.)
+// One thread per (voxel, offset): a warp probes ONE kernel offset for 32 consecutive voxels, a block
+// (27 warps) covers all offsets of those voxels.  Compared with a thread that loops over offsets
+// this keeps no per-offset state in registers (full occupancy), has no predicated-off work, and a
+// collision chain only stalls the 32 probes that share its warp.  The warp's hit ballot is the
+// column of mask bits of its offset; thread v < 32 assembles voxel v's mask word from the 27
+// ballots.  Rows of the table are also staged in shared memory for the row-major copy.
+constexpr int K3_VOX = 32;                     // voxels per block; block = 27 * K3_VOX threads
+__global__ void __launch_bounds__(27 * K3_VOX)
 subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices, int64_t N,
                      int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
-                     uint32_t *__restrict__ mask) {
-    __shared__ uint32_t plane_mask[3][K3_VOX];
-    const int lo = threadIdx.x % K3_VOX;
-    const int rz = threadIdx.x / K3_VOX;          // warp-uniform (K3_VOX is a multiple of 32)
-    const int64_t o = blockIdx.x * (int64_t)K3_VOX + lo;
-    uint32_t mword = 0;
+                     uint32_t *__restrict__ mask, int32_t *__restrict__ row_table) {
+    __shared__ uint32_t hit_col[27];
+    __shared__ int32_t row_stage[K3_VOX][27];     // odd row stride: conflict-free both ways
+    const int lo = threadIdx.x & 31;
+    const int k = threadIdx.x >> 5;               // warp-uniform kernel offset, k = (rz*3 + ry)*3 + rx
+    const int rz = k / 9, ry = (k / 3) % 3, rx = k % 3;
+    const int64_t vbase = blockIdx.x * (int64_t)K3_VOX;
+    const int64_t o = vbase + lo;
+    int32_t found = -1;
     if (o < N) {
         const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + o);    // (b, z, y, x)
         const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
-        const int dz = g.dilation[0], dy = g.dilation[1], dx = g.dilation[2];
         // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
-        const int qz = c.y + (rz - 1) * dz;
-        const bool vz = c.x >= 0 && c.x < g.batch && qz >= 0 && qz < D0;
-        bool vy[3], vx[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int qy = c.z + (r - 1) * dy, qx = c.w + (r - 1) * dx;
-            vy[r] = qy >= 0 && qy < D1;
-            vx[r] = qx >= 0 && qx < D2;
-        }
-        const int sy = dy * D2, sx = dx;
-        const uint32_t key_p = (uint32_t)(((c.x * D0 + c.y) * D1 + c.z) * D2 + c.w) + (uint32_t)((rz - 1) * dz * D1 * D2);
-        unsigned long long slot[9];
-        uint32_t key[9], hpos[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const int ry = j / 3, rx = j % 3;
-            const bool valid = vz && vy[ry] && vx[rx] && !(rz == 1 && j == 4);
-            key[j] = key_p + (uint32_t)((ry - 1) * sy + (rx - 1) * sx);
-            hpos[j] = mix32(key[j]) & table.cap_mask;
-            slot[j] = valid ? __ldg(&table.slots[hpos[j]]) : Table32::EMPTY;
-        }
-        // collision chains advance in ROUNDS: every unresolved probe of the thread steps to its next
-        // slot in the same round, so a warp pays max-chain-length L2 round trips, not their sum
-        uint32_t pending = 0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-            if (slot[j] != Table32::EMPTY && (uint32_t)(slot[j] >> 32) != key[j]) pending |= 1u << j;
-        while (pending) {
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                if (pending & (1u << j)) {
-                    hpos[j] = (hpos[j] + 1) & table.cap_mask;
-                    slot[j] = __ldg(&table.slots[hpos[j]]);
-                }
+        const int qz = c.y + (rz - 1) * g.dilation[0];
+        const int qy = c.z + (ry - 1) * g.dilation[1];
+        const int qx = c.w + (rx - 1) * g.dilation[2];
+        const bool valid = c.x >= 0 && c.x < g.batch && qz >= 0 && qz < D0 && qy >= 0 && qy < D1 && qx >= 0 && qx < D2;
+        if (k == 13) {
+            found = (int32_t)o;                       // centre: identity
+        } else if (valid) {
+            const uint32_t key = (uint32_t)(((c.x * D0 + qz) * D1 + qy) * D2 + qx);
+            uint32_t h = mix32(key) & table.cap_mask;
+            unsigned long long cur = __ldg(&table.slots[h]);
+            while (cur != Table32::EMPTY) {           // collision chain (short at load factor <= 0.25)
+                if ((uint32_t)(cur >> 32) == key) { found = (int32_t)(uint32_t)cur; break; }
+                h = (h + 1) & table.cap_mask;
+                cur = __ldg(&table.slots[h]);
             }
-#pragma unroll
-            for (int j = 0; j < 9; ++j)
-                if ((pending & (1u << j)) && (slot[j] == Table32::EMPTY || (uint32_t)(slot[j] >> 32) == key[j]))
-                    pending &= ~(1u << j);
         }
+        pair_fwd[(int64_t)k * N + o] = found;
+        if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
+    }
+    const uint32_t hits = __ballot_sync(0xffffffffu, found >= 0);
+    if (lo == 0) hit_col[k] = hits;
+    row_stage[lo][k] = found;
+    __syncthreads();
+    if (mask && k == 0 && o < N) {
+        uint32_t m = 0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const int k = rz * 9 + j;
-            int32_t found = slot[j] != Table32::EMPTY ? (int32_t)(uint32_t)slot[j] : -1;
-            if (k == 13) found = (int32_t)o;              // centre: identity
-            pair_fwd[(int64_t)k * N + o] = found;
-            if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
-            if (found >= 0) mword |= 1u << k;
+        for (int kk = 0; kk < 27; ++kk) m |= ((hit_col[kk] >> lo) & 1u) << kk;
+        mask[o] = m;
+    }
+    if (row_table) {
+        // row-major copy [N][32] (one 128-byte line per voxel, -1 padded) for spx_build_tile_table:
+        // the permuted re-read then costs 4 sectors per row instead of one per (row, offset)
+        for (int e = threadIdx.x; e < K3_VOX * 32; e += 27 * K3_VOX) {
+            const int v = e >> 5, kk = e & 31;
+            if (vbase + v < N) row_table[(vbase + v) * 32 + kk] = kk < 27 ? row_stage[v][kk] : -1;
         }
     }
-    if (!mask) return;                                  // uniform over the grid
-    plane_mask[rz][lo] = mword;
-    __syncthreads();
-    if (rz == 0 && o < N) mask[o] = plane_mask[0][lo] | plane_mask[1][lo] | plane_mask[2][lo];
 }
 
 // ------------------------------------------------------------------ regular / transposed conv
@@ -335,37 +323,104 @@ __device__ __forceinline__ bool conv_out_coord(const Geom &g, const int (&c)[SPX
     return valid;
 }
 
-// grid (ceil(N/T), kv): hash every hit, payload = k*N + i (first touch in offset-major order)
-template <typename Table>
-__global__ void conv_insert_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int k = blockIdx.y;
-    int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
-    load_coord(indices, i, g.ndim, c);
-    offset_taps(k, g.ksize, g.ndim, r);
-    if (conv_out_coord(g, c, r, o))
-        table.insert_min(linear_key(o, g.out_dims, g.ndim), (int32_t)((int64_t)k * N + i));
+// 3-D, non-transposed fast path of query_npq (indices.py:141-203): the taps of the block's offset
+// are decoded once per block, the stride division is a shift for strides 1 and 2, everything else
+// is three fused range tests.  (The generic helpers spend ~150 instructions per (input, offset)
+// on run-time-ndim loops and two integer divisions per axis.)
+struct Taps3 { int r0, r1, r2; };
+__device__ __forceinline__ Taps3 block_taps3(const Geom &g, int k) {
+    Taps3 t;
+    t.r2 = k % g.ksize[2]; k /= g.ksize[2];
+    t.r1 = k % g.ksize[1]; k /= g.ksize[1];
+    t.r0 = k;
+    return t;
+}
+__device__ __forceinline__ bool axis_out(int c, int pad, int r, int dil, int stride, int odim, int &o) {
+    const int h = c + pad - r * dil;
+    if (h < 0) return false;
+    if (stride == 1) o = h;
+    else if (stride == 2) { if (h & 1) return false; o = h >> 1; }
+    else { o = h / stride; if (o * stride != h) return false; }
+    return o < odim;
+}
+__device__ __forceinline__ bool conv3_out_key(const Geom &g, const int4 c, const Taps3 &t, int64_t &key) {
+    int o0, o1, o2;
+    if (c.x < 0 || c.x >= g.batch) return false;
+    if (!axis_out(c.y, g.padding[0], t.r0, g.dilation[0], g.stride[0], g.out_dims[0], o0)) return false;
+    if (!axis_out(c.z, g.padding[1], t.r1, g.dilation[1], g.stride[1], g.out_dims[1], o1)) return false;
+    if (!axis_out(c.w, g.padding[2], t.r2, g.dilation[2], g.stride[2], g.out_dims[2], o2)) return false;
+    key = (((int64_t)c.x * g.out_dims[0] + o0) * g.out_dims[1] + o1) * g.out_dims[2] + o2;
+    return true;
 }
 
-// compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next)
+// grid (ceil(N/T), kv): hash every hit, payload = k*N + i (first touch in offset-major order)
+template <typename Table, bool FAST3>
+__global__ void conv_insert_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if constexpr (FAST3) {
+        __shared__ Taps3 taps;
+        if (threadIdx.x == 0) taps = block_taps3(g, k);
+        __syncthreads();
+        if (i >= N) return;
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+        int64_t key;
+        if (conv3_out_key(g, c, taps, key)) table.insert_min(key, (int32_t)((int64_t)k * N + i));
+    } else {
+        if (i >= N) return;
+        int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
+        load_coord(indices, i, g.ndim, c);
+        offset_taps(k, g.ksize, g.ndim, r);
+        if (conv_out_coord(g, c, r, o))
+            table.insert_min(linear_key(o, g.out_dims, g.ndim), (int32_t)((int64_t)k * N + i));
+    }
+}
+
+// compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next).
+// The table is sized for the worst-case output count, so most of it is empty: every thread scans
+// COLLECT_ITEMS slots and a block reserves its output range with ONE atomic (a single global
+// counter takes ~2.7 G same-address atomics/s on B200; one per warp made this kernel the slowest
+// of the conv rulebook).
+constexpr int COLLECT_THREADS = 256;
+constexpr int COLLECT_ITEMS = 4;
 template <typename Table>
-__global__ void conv_collect_kernel(Table table, uint32_t capacity, uint32_t *__restrict__ payload,
-                                    uint32_t *__restrict__ slot_of, int *__restrict__ counter) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    bool occ = false;
-    int64_t key; int32_t val = 0;
-    if (s < capacity) occ = table.occupied(s, key, val);
-    unsigned ballot = __ballot_sync(0xffffffffu, occ);
-    if (ballot == 0) return;
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (occ) {
-        int pos = base + __popc(ballot & ((1u << lane) - 1));
-        payload[pos] = (uint32_t)val;
-        slot_of[pos] = s;
+__global__ void __launch_bounds__(COLLECT_THREADS)
+conv_collect_kernel(Table table, uint32_t capacity, uint32_t *__restrict__ payload,
+                    uint32_t *__restrict__ slot_of, int *__restrict__ counter) {
+    __shared__ int warp_cnt[COLLECT_THREADS / 32];
+    __shared__ int block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = blockIdx.x * (uint32_t)(COLLECT_THREADS * COLLECT_ITEMS);
+    bool occ[COLLECT_ITEMS];
+    int32_t val[COLLECT_ITEMS];
+    unsigned ballot[COLLECT_ITEMS];
+    int mine = 0;                                   // occupied slots seen by this warp
+#pragma unroll
+    for (int j = 0; j < COLLECT_ITEMS; ++j) {
+        const uint32_t s = first + j * COLLECT_THREADS + threadIdx.x;
+        int64_t key;
+        val[j] = 0;
+        occ[j] = s < capacity && table.occupied(s, key, val[j]);
+        ballot[j] = __ballot_sync(0xffffffffu, occ[j]);
+        mine += __popc(ballot[j]);
+    }
+    if (lane == 0) warp_cnt[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < COLLECT_THREADS / 32; ++w) { const int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+        block_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    int base = block_base + warp_cnt[warp];
+#pragma unroll
+    for (int j = 0; j < COLLECT_ITEMS; ++j) {
+        if (occ[j]) {
+            const int pos = base + __popc(ballot[j] & ((1u << lane) - 1));
+            payload[pos] = (uint32_t)val[j];
+            slot_of[pos] = first + j * COLLECT_THREADS + threadIdx.x;
+        }
+        base += __popc(ballot[j]);
     }
 }
 
@@ -388,19 +443,30 @@ __global__ void conv_assign_kernel(Table table, Geom g, const uint32_t *__restri
 }
 
 // grid (ceil(N/T), kv): pair_bwd[k][i] = o (every element written), pair_fwd[k][o] = i
-template <typename Table>
+template <typename Table, bool FAST3>
 __global__ void conv_pairs_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N, int64_t M,
                                   int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= N) return;
     int k = blockIdx.y;
-    int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
-    load_coord(indices, i, g.ndim, c);
-    offset_taps(k, g.ksize, g.ndim, r);
     int32_t out = -1;
-    if (conv_out_coord(g, c, r, o)) {
+    if constexpr (FAST3) {
+        __shared__ Taps3 taps;
+        if (threadIdx.x == 0) taps = block_taps3(g, k);
+        __syncthreads();
+        if (i >= N) return;
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+        int64_t key;
         int32_t v;
-        if (table.find_slot(linear_key(o, g.out_dims, g.ndim), v) >= 0) out = v;
+        if (conv3_out_key(g, c, taps, key) && table.find_slot(key, v) >= 0) out = v;
+    } else {
+        if (i >= N) return;
+        int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
+        load_coord(indices, i, g.ndim, c);
+        offset_taps(k, g.ksize, g.ndim, r);
+        if (conv_out_coord(g, c, r, o)) {
+            int32_t v;
+            if (table.find_slot(linear_key(o, g.out_dims, g.ndim), v) >= 0) out = v;
+        }
     }
     pair_bwd[(int64_t)k * N + i] = out;
     if (out >= 0) pair_fwd[(int64_t)k * M + out] = (int32_t)i;
@@ -586,6 +652,102 @@ build_tile_table_kernel(const int32_t *__restrict__ pair, int64_t pair_stride, i
                                                                   red[threadIdx.x][2] | red[threadIdx.x][3];
 }
 
+// same table from the row-major copy [rows][32] written by subm_probe_k3_kernel (kv <= 32):
+// 4 threads per row, two 16-byte loads each, stores coalesced over the rows of the tile
+__global__ void __launch_bounds__(128 * TT_SPLIT)
+build_tile_table_rows_kernel(const int32_t *__restrict__ row_table, int kv, const int32_t *__restrict__ argsort,
+                             const uint32_t *__restrict__ mask, int64_t rows, int32_t *__restrict__ table,
+                             uint32_t *__restrict__ tile_mask) {
+    const int64_t t = blockIdx.x;
+    const int r = threadIdx.x & 127;
+    const int q = threadIdx.x >> 7;
+    const int64_t j = t * 128 + r;
+    int32_t src = -1;
+    if (j < rows) src = argsort ? __ldg(argsort + j) : (int32_t)j;
+    int32_t *blk = table + t * (int64_t)(kv + 1) * 128;
+    int4 v0 = make_int4(-1, -1, -1, -1), v1 = v0;
+    if (src >= 0) {
+        const int4 *rp = reinterpret_cast<const int4 *>(row_table + (int64_t)src * 32 + q * 8);
+        v0 = __ldg(rp); v1 = __ldg(rp + 1);
+    }
+    const int32_t vals[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = q * 8 + i;
+        if (k < kv) blk[k * 128 + r] = vals[i];
+    }
+    if (q == 0) blk[kv * 128 + r] = src;
+    __shared__ uint32_t red[4];
+    if (q == 0) {
+        uint32_t m = 0;
+        if (j < rows) m = mask ? __ldg(mask + j) : (kv >= 32 ? 0xffffffffu : ((1u << kv) - 1u));
+        m = __reduce_or_sync(0xffffffffu, m);
+        if ((r & 31) == 0) red[r >> 5] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tile_mask[t] = red[0] | red[1] | red[2] | red[3];
+}
+
+// Schedule records for the dynamically scheduled kernels: tiles in order of decreasing stage count
+// (= popcount of the tile mask), ties in ascending tile order (stable => deterministic).  Handing
+// tiles out heaviest-first through an atomic ticket is LPT list scheduling: on the 100 k-voxel
+// cloud the static round-robin assignment leaves the slowest CTA 1.6x over the mean, LPT 1.07x.
+// One block; chunks of 1024 tiles are ranked with warp match_any + per-warp bucket counts.
+constexpr int TO_THREADS = 1024;
+constexpr int TO_BUCKETS = 130;                 // stage counts 0..128 (+1 spare)
+__global__ void __launch_bounds__(TO_THREADS)
+tile_order_kernel(const uint32_t *__restrict__ tile_mask, int tiles, int words, int32_t *__restrict__ rec,
+                  int32_t *__restrict__ state) {
+    __shared__ int bucket_base[TO_BUCKETS];
+    __shared__ int wcnt[TO_THREADS / 32][TO_BUCKETS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < TT_STATE_INTS) state[tid] = 0;
+    for (int i = tid; i < TO_BUCKETS; i += TO_THREADS) bucket_base[i] = 0;
+    __syncthreads();
+    auto load_mask = [&](int t, uint32_t (&m)[4]) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { m[w] = w < words ? __ldg(tile_mask + (int64_t)t * words + w) : 0u; any |= m[w]; }
+        if (!any) m[0] = 1u;                     // an empty tile still runs one (all-zero) stage
+        return __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+    };
+    // bucket sizes
+    for (int t = tid; t < tiles; t += TO_THREADS) {
+        uint32_t m[4];
+        atomicAdd(&bucket_base[load_mask(t, m)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {                               // exclusive scan, heaviest bucket first
+        int run = 0;
+        for (int c = TO_BUCKETS - 1; c >= 0; --c) { const int n = bucket_base[c]; bucket_base[c] = run; run += n; }
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < tiles; t0 += TO_THREADS) {
+        for (int i = tid; i < (TO_THREADS / 32) * TO_BUCKETS; i += TO_THREADS) (&wcnt[0][0])[i] = 0;
+        __syncthreads();
+        const int t = t0 + tid;
+        const bool ok = t < tiles;
+        uint32_t m[4] = {0, 0, 0, 0};
+        const int c = ok ? load_mask(t, m) : TO_BUCKETS - 1;
+        const unsigned peers = __match_any_sync(0xffffffffu, ok ? c : -1);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (ok && rank == 0) wcnt[warp][c] = __popc(peers);
+        __syncthreads();
+        for (int b = tid; b < TO_BUCKETS; b += TO_THREADS) {
+            int run = bucket_base[b];
+            for (int w = 0; w < TO_THREADS / 32; ++w) { const int n = wcnt[w][b]; wcnt[w][b] = run; run += n; }
+            bucket_base[b] = run;
+        }
+        __syncthreads();
+        if (ok) {
+            int32_t *r = rec + (int64_t)(wcnt[warp][c] + rank) * TT_REC_INTS;
+            *reinterpret_cast<int4 *>(r) = make_int4(t, (int)m[0], (int)m[1], (int)m[2]);
+            *reinterpret_cast<int4 *>(r + 4) = make_int4((int)m[3], 0, 0, 0);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -655,9 +817,18 @@ extern "C" size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_
     return total + 1024;
 }
 
+static bool subm_k3_path(const Geom &gg) {
+    return !needs_i64(gg, gg.in_dims) && gg.ndim == 3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
+}
+
+extern "C" int spx_subm_row_table_supported(const spx_conv_geometry *g) {
+    if (!g || g->ndim < 1 || g->ndim > SPX_MAX_NDIM) return 0;
+    return subm_k3_path(make_geom(g, true)) ? 1 : 0;
+}
+
 extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indices, int64_t N, int32_t *pair_fwd,
-                                 int32_t *pair_bwd, uint32_t *mask, void *workspace, size_t workspace_bytes,
-                                 spx_stream_t stream_) {
+                                 int32_t *pair_bwd, uint32_t *mask, int32_t *row_table, void *workspace,
+                                 size_t workspace_bytes, spx_stream_t stream_) {
     if (validate_geom(g)) return 2;
     for (int a = 0; a < g->ndim; ++a)
         SPX_REQUIRE(g->ksize[a] % 2 == 1, "subm only support odd ksize");
@@ -680,10 +851,11 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
         Table32 t{(unsigned long long *)tbl, L.capacity - 1};
         subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("subm_insert_kernel");
-        if (gg.ndim == 3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3) {
-            subm_probe_k3_kernel<<<(unsigned)div_up64(N, K3_VOX), 3 * K3_VOX, 0, stream>>>(t, gg, indices, N, pair_fwd,
-                                                                                           pair_bwd, mask);
+        if (subm_k3_path(gg)) {
+            subm_probe_k3_kernel<<<(unsigned)div_up64(N, K3_VOX), 27 * K3_VOX, 0, stream>>>(t, gg, indices, N, pair_fwd,
+                                                                                            pair_bwd, mask, row_table);
         } else {
+            SPX_REQUIRE(row_table == nullptr, "row_table is only produced when spx_subm_row_table_supported()");
             subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
         }
         SPX_CHECK_LAUNCH("subm_probe_kernel");
@@ -692,6 +864,7 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
         Table64 t{(long long *)tbl, tvals, L.capacity - 1};
         subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("subm_insert_kernel");
+        SPX_REQUIRE(row_table == nullptr, "row_table is only produced when spx_subm_row_table_supported()");
         subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
         SPX_CHECK_LAUNCH("subm_probe_kernel");
     }
@@ -741,21 +914,24 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
     if (carve_conv_ws(g, gg, N, workspace, workspace_bytes, w)) return 2;
     const int T = 128;
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
+    const bool fast3 = gg.ndim == 3 && !gg.transposed;
     SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
     SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
-    unsigned cblk = (w.L.capacity + 255) / 256;
+    unsigned cblk = (unsigned)div_up64(w.L.capacity, COLLECT_THREADS * COLLECT_ITEMS);
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
-        conv_insert_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N);
+        if (fast3) conv_insert_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
+        else conv_insert_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("conv_insert_kernel");
-        conv_collect_kernel<<<cblk, 256, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
+        conv_collect_kernel<<<cblk, COLLECT_THREADS, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
         SPX_CHECK_LAUNCH("conv_collect_kernel");
     } else {
         SPX_CHECK_CUDA(cudaMemsetAsync(w.tvals, 0x7F, (size_t)w.L.capacity * 4, stream));
         Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
-        conv_insert_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N);
+        if (fast3) conv_insert_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
+        else conv_insert_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("conv_insert_kernel");
-        conv_collect_kernel<<<cblk, 256, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
+        conv_collect_kernel<<<cblk, COLLECT_THREADS, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
         SPX_CHECK_LAUNCH("conv_collect_kernel");
     }
     int m_host = 0;
@@ -787,18 +963,21 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
     int words = (gg.kv + 31) / 32;
     const int T = 128;
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
+    const bool fast3 = gg.ndim == 3 && !gg.transposed;
     SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        conv_pairs_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        else conv_pairs_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     } else {
         Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        conv_pairs_kernel<<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        else conv_pairs_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     }
     if (mask_fwd) {
@@ -932,19 +1111,33 @@ extern "C" int spx_mask_argsort(uint32_t *mask, int32_t *argsort, int64_t N, int
 }
 
 extern "C" size_t spx_tile_table_elems(int64_t rows, int kv) {
-    return (size_t)div_up64(rows > 0 ? rows : 1, 128) * (size_t)(kv + 1) * 128;
+    return (size_t)tt_total_elems(div_up64(rows > 0 ? rows : 1, 128), kv);
 }
 
 extern "C" int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, int kv, const int32_t *argsort,
-                                    const uint32_t *mask, int64_t rows, int32_t *table, uint32_t *tile_mask,
-                                    spx_stream_t stream_) {
+                                    const uint32_t *mask, int64_t rows, const int32_t *row_table, int32_t *table,
+                                    uint32_t *tile_mask, spx_stream_t stream_) {
     SPX_REQUIRE(kv >= 1 && kv <= 128, "build_tile_table: kernel volume %d not in [1,128]", kv);
     if (rows == 0) return 0;
-    SPX_REQUIRE(pair && table && tile_mask, "build_tile_table: NULL pointer argument");
+    SPX_REQUIRE((pair || row_table) && table && tile_mask, "build_tile_table: NULL pointer argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     int words = (kv + 31) / 32;
-    build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128 * TT_SPLIT, 0, stream>>>(pair, pair_stride, kv, argsort, mask,
-                                                                             rows, words, table, tile_mask);
-    SPX_CHECK_LAUNCH("build_tile_table_kernel");
+    if (row_table) {
+        SPX_REQUIRE(kv <= 32, "build_tile_table: row_table holds at most 32 offsets per row, kv = %d", kv);
+        SPX_REQUIRE(((uintptr_t)row_table & 15u) == 0, "build_tile_table: row_table must be 16-byte aligned");
+        build_tile_table_rows_kernel<<<(unsigned)div_up64(rows, 128), 128 * TT_SPLIT, 0, stream>>>(
+            row_table, kv, argsort, mask, rows, table, tile_mask);
+        SPX_CHECK_LAUNCH("build_tile_table_rows_kernel");
+    } else {
+        build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128 * TT_SPLIT, 0, stream>>>(
+            pair, pair_stride, kv, argsort, mask, rows, words, table, tile_mask);
+        SPX_CHECK_LAUNCH("build_tile_table_kernel");
+    }
+    const int64_t tiles = div_up64(rows, 128);
+    SPX_REQUIRE(tiles < 2147483647ll, "build_tile_table: too many tiles");
+    SPX_REQUIRE(((uintptr_t)table & 15u) == 0, "build_tile_table: table must be 16-byte aligned");
+    int32_t *rec = table + tt_blocks_elems(tiles, kv);
+    tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(tile_mask, (int)tiles, words, rec, rec + tiles * TT_REC_INTS);
+    SPX_CHECK_LAUNCH("tile_order_kernel");
     return 0;
 }

@@ -186,7 +186,7 @@ def get_indice_pairs(indices: torch.Tensor, batch_size: int, spatial_shape: List
         pair_bwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
         ws = _bytes(lib.spx_rulebook_workspace_size(ctypes.byref(geo), n_in, 0, 1), dev)
         _cabi.check(lib.spx_subm_rulebook(ctypes.byref(geo), _ptr(indices), n_in,
-                                          pair_fwd.data_ptr(), pair_bwd.data_ptr(), None,
+                                          pair_fwd.data_ptr(), pair_bwd.data_ptr(), None, None,
                                           ws.data_ptr(), ws.numel(), _stream()), "subm_rulebook")
         out_inds = indices
     else:
@@ -235,18 +235,25 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
                 raise RuntimeError("subm only support odd ksize")
         pair = torch.empty((2 if is_train else 1, kv, n_in), dtype=torch.int32, device=dev)
         pair_mask = torch.empty((1, n_in, words), dtype=torch.int32, device=dev)
+        # row-major by-product of the probe kernel; consumed (and dropped) by the first tile-table build
+        rows = None
+        if n_in and lib.spx_subm_row_table_supported(ctypes.byref(geo)):
+            rows = torch.empty((n_in, 32), dtype=torch.int32, device=dev)
         with timer.record("gen_subm_inds", _stream()):
             ws = _bytes(lib.spx_rulebook_workspace_size(ctypes.byref(geo), n_in, 0, 1), dev, alloc)
             _cabi.check(lib.spx_subm_rulebook(ctypes.byref(geo), _ptr(indices), n_in,
                                               pair[0].data_ptr(),
                                               pair[1].data_ptr() if is_train and n_in else None,
-                                              _ptr(pair_mask), ws.data_ptr(), ws.numel(),
+                                              _ptr(pair_mask), _ptr(rows), ws.data_ptr(), ws.numel(),
                                               _stream()), "subm_rulebook")
         with timer.record("gen_subm_inds_sort", _stream()):
             mask_argsort = _argsort_masks(pair_mask, kv, do_sort, alloc)
+        argsort_view = mask_argsort[0]
+        if rows is not None:
+            argsort_view._spx_row_table = (pair[0].data_ptr(), rows)
         pair_bwd = pair[1] if is_train else torch.Tensor()
         return (indices, indice_num_per_loc, pair[0], pair_bwd, [pair_mask[0]], [],
-                [mask_argsort[0]], [], masks)
+                [argsort_view], [], masks)
     with timer.record("gen_conv_inds", _stream()):
         out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd = _conv_rulebook(
             geo, indices, n_in, kv, words, True, alloc)
@@ -283,9 +290,15 @@ def _tile_tables(pair: torch.Tensor, mask: Optional[torch.Tensor], argsort: Opti
     tiles = max((int(rows) + MASK_WIDTH - 1) // MASK_WIDTH, 1)
     table = torch.empty((lib.spx_tile_table_elems(int(rows), kv),), dtype=torch.int32, device=pair.device)
     tile_mask = torch.empty((tiles, words), dtype=torch.int32, device=pair.device)
+    row_table = None
+    hint = getattr(owner, "_spx_row_table", None) if owner is not None else None
+    if hint is not None and hint[0] == pair.data_ptr() and hint[1].shape[0] == int(rows):
+        row_table = hint[1]
     _cabi.check(lib.spx_build_tile_table(_ptr(pair), int(pair.stride(0)), kv, _ptr(argsort), _ptr(mask),
-                                         int(rows), _ptr(table), _ptr(tile_mask), _stream()),
+                                         int(rows), _ptr(row_table), _ptr(table), _ptr(tile_mask), _stream()),
                 "build_tile_table")
+    if hint is not None:
+        owner._spx_row_table = None                # one-shot: 128 B per voxel are not kept alive
     if owner is not None:
         owner._spx_tile_cache = (key, table, tile_mask)
     return table, tile_mask

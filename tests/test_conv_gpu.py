@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import describe_mismatch, random_cloud, rel_l2
+from tests.util import describe_mismatch, random_cloud, rel_l2, surface_cloud
 
 pytestmark = pytest.mark.gpu
 
@@ -251,3 +251,32 @@ def test_int8_inference_forward(CK, subm, out_int8, oracle, cuda_dev):
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (diff.max(), (diff > 0).mean())
     else:
         assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_dynamic_scheduler_leaves_state_clean_and_is_repeatable(cuda_dev):
+    """The tcgen05 forward / input-gradient kernels draw tiles from an atomic ticket counter that
+    lives behind the tile table; every launch must leave it zeroed (the last CTA resets it), and
+    repeated launches must give bit-identical results whatever CTA ran which tile."""
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(11)
+    shape = [24, 400, 352]
+    inds = torch.from_numpy(surface_cloud(rng, shape, 40000)).to(cuda_dev)
+    n = inds.shape[0]
+    res = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3,
+                                             [1] * 3, [1] * 3, [0] * 3, True, False, is_train=True)
+    _, _, pf, pb, mf, mb, sf, sb, masks = res
+    g = torch.Generator(device=cuda_dev).manual_seed(3)
+    x = (torch.rand((n, 64), device=cuda_dev, generator=g) - 0.5).half()
+    w = ((torch.rand((64, 3, 3, 3, 64), device=cuda_dev, generator=g) - 0.5) * 0.2).half()
+    dout = (torch.rand((n, 64), device=cuda_dev, generator=g) - 0.5).half()
+    outs, dins = [], []
+    for _ in range(5):
+        out, mask_out, mw = ops.implicit_gemm(x, w, pf, mf, sf, n, masks, True, True)
+        din, dw = ops.implicit_gemm_backward(x, w, dout, pf, pb, mf, mb, sf, sb, mask_out, masks, mw, True)
+        outs.append(out); dins.append(din)
+    torch.cuda.synchronize()
+    table = sf[0]._spx_tile_cache[1]
+    assert (table[-64:] == 0).all(), "scheduler scratch must be zero between launches"
+    for o, d in zip(outs[1:], dins[1:]):
+        assert torch.equal(o, outs[0]) and torch.equal(d, dins[0])

@@ -182,3 +182,51 @@ def test_vanished_points_error(cuda_dev):
     with pytest.raises(RuntimeError, match="odd ksize"):
         ops.get_indice_pairs(inds, 1, [8, 8, 8], ConvAlgo.Native, [2] * 3, [1] * 3, [0] * 3,
                              [1] * 3, [0] * 3, True)
+
+
+def test_tile_table_from_row_table_matches_column_path(cuda_dev):
+    """spx_build_tile_table has two sources for the same table: the column-major pair table and
+    the row-major by-product of the 3x3x3 probe kernel.  Both must give identical blocks and
+    tile masks (== per-tile OR of the sorted masks, the reference's mask_output_fwd with
+    mask_width 128, spconv/csrc/sparse/convops.py:2180-2189)."""
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(5)
+    shape = [24, 200, 176]
+    inds = torch.from_numpy(surface_cloud(rng, shape, 9000 + 77)).to(cuda_dev)
+    n = inds.shape[0]
+    res = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3,
+                                             [1] * 3, [1] * 3, [0] * 3, True, False, is_train=True)
+    pair_fwd, mask, argsort = res[2], res[4][0], res[6][0]
+    hint = getattr(argsort, "_spx_row_table", None)
+    assert hint is not None, "3x3x3 SubM rulebook must hand the row-major table to the tile builder"
+    rows = hint[1].cpu().numpy()
+    pf = pair_fwd.cpu().numpy()
+    assert np.array_equal(rows[:, :27], pf.T) and (rows[:, 27:] == -1).all()
+    t_rows, m_rows = ops._tile_tables(pair_fwd, mask, argsort, n, 27, owner=argsort)
+    assert argsort._spx_row_table is None                       # consumed
+    t_cols, m_cols = ops._tile_tables(pair_fwd, mask, argsort, n, 27, owner=None)
+    assert torch.equal(t_rows, t_cols) and torch.equal(m_rows, m_cols)
+    tiles = (n + 127) // 128
+    flat = t_cols.cpu().numpy()
+    tab = flat[:tiles * 28 * 128].reshape(tiles, 28, 128)
+    order = argsort.cpu().numpy()
+    padded = np.full(tiles * 128, -1, np.int64)
+    padded[:n] = order
+    assert np.array_equal(tab[:, 27, :].reshape(-1), padded)
+    want = np.where(padded[None, :] >= 0, pf[:, np.maximum(padded, 0)], -1)            # [27, tiles*128]
+    assert np.array_equal(tab[:, :27, :].transpose(1, 0, 2).reshape(27, -1), want)
+    sm = np.zeros(tiles * 128, np.uint32)
+    sm[:n] = mask.cpu().numpy().reshape(-1).view(np.uint32)
+    assert np.array_equal(m_cols.cpu().numpy().reshape(-1).view(np.uint32),
+                          np.bitwise_or.reduce(sm.reshape(tiles, 128), axis=1))
+    # schedule records behind the blocks: every tile once, heaviest (most offsets) first, ties in
+    # ascending tile order; scheduler scratch zeroed
+    rec = flat[tiles * 28 * 128: tiles * 28 * 128 + tiles * 8].reshape(tiles, 8)
+    tmask = m_cols.cpu().numpy().reshape(-1).view(np.uint32)
+    cost = np.array([bin(int(v)).count("1") for v in np.where(tmask == 0, 1, tmask)])
+    want_order = np.argsort(-cost, kind="stable")
+    assert np.array_equal(rec[:, 0], want_order)
+    assert np.array_equal(rec[:, 1].view(np.uint32), np.where(tmask == 0, 1, tmask)[want_order])
+    assert (rec[:, 2:] == 0).all()
+    assert (flat[tiles * 28 * 128 + tiles * 8:] == 0).all() and flat.shape[0] == tiles * 28 * 128 + tiles * 8 + 64

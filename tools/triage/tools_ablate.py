@@ -18,7 +18,7 @@ def t(fn,n=20):
     for _ in range(3): fn()
     tot=0
     for _ in range(n):
-        flush.zero_(); a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
+        flush.zero_(); torch.cuda._sleep(600000); a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); tot+=a.elapsed_time(b)
     return tot/n*1000
 res_all={}
