@@ -75,6 +75,13 @@ __device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ t
     for (int w = 0; w < 4; ++w) out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
 }
 
+__device__ __forceinline__ long long wg_global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// per-CTA wall-clock spans (ns): row 2 of the trace buffer holds [pass * chunks + chunk][4]
+#define WG_SPAN(i) do { if (p.dbg_ts && threadIdx.x == 0) { const int c_ = blockIdx.y * gridDim.x + blockIdx.x; if (c_ < 512) p.dbg_ts[2 * 2048 + c_ * 4 + (i)] = wg_global_ns(); } } while (0)
 #define WG_STAMP(role, n) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (n) < 2048) p.dbg_ts[(role) * 2048 + (n)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t pick_word(const uint32_t (&m)[4], int w) {
@@ -98,6 +105,7 @@ tc_wgrad_kernel(const WgParams p) {
     constexpr int ITERS = ROWS_PW / RPI > 0 ? ROWS_PW / RPI : 1;   // cp.async per thread per atom
     constexpr int ITERS_D = ROWS_PW / RPI_D;                       // cp.async per thread per dout tile
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    WG_SPAN(0);
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t *smem = smem_raw + pad;
@@ -122,14 +130,17 @@ tc_wgrad_kernel(const WgParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t num_tiles = (p.rows + WG_TILE - 1) / WG_TILE;
     const int chunk = blockIdx.x, chunks = gridDim.x;
-    const int g_begin = blockIdx.y * p.groups_per_pass;
-    const int g_end = min(p.groups_total, g_begin + p.groups_per_pass);
+    // Groups are dealt to the passes round-robin (pass y owns groups y, y + passes, ...): with the
+    // mirror-paired slot order the frequently active in-plane offsets sit in neighbouring groups,
+    // and a contiguous split gave one pass 70 % of the stages of the 100 k-voxel cloud.
+    const int g_first = blockIdx.y, g_step = gridDim.y;
+    const int ng = g_first < p.groups_total ? (p.groups_total - g_first + g_step - 1) / g_step : 0;
 
     if (threadIdx.x < 32) {
         // group gl covers atoms [g*apg, (g+1)*apg) -> offset slots a / apo; one thread per group
-        const int g = g_begin + (int)threadIdx.x;
+        const int g = g_first + (int)threadIdx.x * g_step;
         uint32_t m[4] = {0, 0, 0, 0};
-        if (g < g_end) {
+        if ((int)threadIdx.x < ng) {
             for (int a = g * p.apg; a < (g + 1) * p.apg; ++a) {
                 const int k = slot_offset(a / p.apo, p.kv);
                 if (k < p.kv) m[k >> 5] |= 1u << (k & 31);
@@ -156,6 +167,7 @@ tc_wgrad_kernel(const WgParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (warp == 0) WG_STAMP(3, 0);
+    WG_SPAN(1);
 
     if (warp >= 4 && warp < WG_MMA_WARP) {
         // ================================================= producers
@@ -237,7 +249,7 @@ tc_wgrad_kernel(const WgParams p) {
             wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
             if (tile + chunks < num_tiles) wg_load_tile_mask(p.tile_mask, tile + chunks, p.words, tm1);
             mbar_wait(&idx_full[0], 0u);
-            act = active_groups(tm, gmask, g_end - g_begin, p.words);
+            act = active_groups(tm, gmask, ng, p.words);
             if (act) issue_b(idx_block(0));
         }
         for (; tile < num_tiles; tile += chunks) {
@@ -252,14 +264,14 @@ tc_wgrad_kernel(const WgParams p) {
             bool next_ready = !has_next;
             auto prepare_next = [&]() {
                 mbar_wait(&idx_full[nxt_slot], nxt_use & 1u);
-                act_next = active_groups(tm1, gmask, g_end - g_begin, p.words);
+                act_next = active_groups(tm1, gmask, ng, p.words);
                 if (act_next) issue_b(idx_block(nxt_slot));
                 next_ready = true;
             };
             const int32_t *idx_s = idx_block(cur_slot);
             // ---- gathered x atoms, one stage per active group
             for (uint32_t rem = act; rem; rem &= rem - 1) {
-                const int g = g_begin + (__ffs(rem) - 1);
+                const int g = g_first + (__ffs(rem) - 1) * g_step;
                 mbar_wait(&empty_a[stage], phase ^ 1u);
                 if (pw == 0) WG_STAMP(0, 2 * nst);
                 const uint32_t a_stage = a_base + (uint32_t)stage * p.a_stage_bytes;
@@ -311,7 +323,7 @@ tc_wgrad_kernel(const WgParams p) {
             const int64_t next = tile + chunks;
             uint32_t tm_next[4] = {0, 0, 0, 0};
             if (next < num_tiles) wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
-            const uint32_t act = active_groups(tm, gmask, g_end - g_begin, p.words);
+            const uint32_t act = active_groups(tm, gmask, ng, p.words);
             if (act) {
                 const int bb = (int)(nb & 1);
                 mbar_wait(&full_b[bb], (uint32_t)((nb >> 1) & 1));
@@ -351,37 +363,54 @@ tc_wgrad_kernel(const WgParams p) {
         __syncwarp();
         tc_commit_elect(acc_done);
         __syncwarp();
-    } else {
-        // ================================================= epilogue: TMEM -> fp32 partials
+    }
+
+    // ================================================= drain: TMEM -> fp32 partials
+    // Twelve warps share it (a warp may touch the TMEM lane quarter warp % 4, so the eight
+    // producer warps, idle by now, drain next to the four epilogue warps); work items are
+    // (group, 32-column block) pairs with both tcgen05.ld in flight before the single wait.
+    if (warp < WG_MMA_WARP) {
         mbar_wait(acc_done, 0);
+        if (warp == 0) WG_SPAN(2);
         tc_fence_after();
         const uint32_t used = *reinterpret_cast<volatile uint32_t *>(used_smem);
-        const int L = warp * 32 + lane;                    // TMEM lane = M index inside the group
+        const int q = warp & 3, helper = warp >> 2;
+        const int L = q * 32 + lane;                       // TMEM lane = M index inside the group
         const int s = L / p.atom_elems;
         const int ce = L - s * p.atom_elems;
         float *part = p.partial + (int64_t)chunk * p.partial_stride;
-        for (int g = g_begin; g < g_end; ++g) {
-            const int gl = g - g_begin;
+        const int nblocks = p.n >> 5;                      // 32-column blocks per group (n % 32 == 0 here)
+        const int tail16 = p.n & 16;                       // one 16-column remainder when n % 32 == 16
+        const int per_group = nblocks + (tail16 ? 1 : 0);
+        int item = 0;
+        for (int gl = 0; gl < ng; ++gl) {
+            const int g = g_first + gl * g_step;
             const int a = g * p.apg + s;
             const int ks = a / p.apo;
             const int k = slot_offset(ks, p.kv);
             const int c = (a - ks * p.apo) * p.atom_elems + ce;
             const bool valid = k < p.kv;
             const bool has = (used >> gl) & 1u;
-            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(gl * p.n);
-            for (int n0 = 0; n0 < p.n; n0 += 16) {
-                uint32_t v[16];
-                if (has) {
-                    tmem_ld_32x32b_x16(t_row + (uint32_t)n0, v);
-                    tc_wait_ld();
-                } else {
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gl * p.n);
+            for (int blk = 0; blk < per_group; ++blk, ++item) {
+                if (item % 3 != helper) continue;
+                const int n0 = blk * 32;
+                const int cols = blk < nblocks ? 32 : 16;
+                uint32_t v[32];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+                if (has) {
+                    uint32_t lo[16], hi[16];
+                    tmem_ld_32x32b_x16(t_row + (uint32_t)n0, lo);
+                    if (cols == 32) tmem_ld_32x32b_x16(t_row + (uint32_t)n0 + 16u, hi);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = cols == 32 ? hi[j] : 0u; }
                 }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        part[((int64_t)(n0 + j) * p.kv + k) * p.c_in + c] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cols) part[((int64_t)(n0 + j) * p.kv + k) * p.c_in + c] = __uint_as_float(v[j]);
                 }
             }
         }
@@ -391,6 +420,7 @@ tc_wgrad_kernel(const WgParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) WG_STAMP(3, 2);
+    WG_SPAN(3);
     if (warp == WG_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

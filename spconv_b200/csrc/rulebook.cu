@@ -717,9 +717,20 @@ tile_order_kernel(const uint32_t *__restrict__ tile_mask, int tiles, int words, 
         atomicAdd(&bucket_base[load_mask(t, m)], 1);
     }
     __syncthreads();
-    if (tid == 0) {                               // exclusive scan, heaviest bucket first
-        int run = 0;
-        for (int c = TO_BUCKETS - 1; c >= 0; --c) { const int n = bucket_base[c]; bucket_base[c] = run; run += n; }
+    if (warp == 0) {                              // exclusive scan, heaviest bucket first (one warp, shuffles)
+        int carry = 0;
+        for (int base = TO_BUCKETS - 1; base >= 0; base -= 32) {
+            const int c = base - lane;
+            const int n = c >= 0 ? bucket_base[c] : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (c >= 0) bucket_base[c] = carry + incl - n;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     __syncthreads();
     for (int t0 = 0; t0 < tiles; t0 += TO_THREADS) {
@@ -733,9 +744,10 @@ tile_order_kernel(const uint32_t *__restrict__ tile_mask, int tiles, int words, 
         const int rank = __popc(peers & ((1u << lane) - 1u));
         if (ok && rank == 0) wcnt[warp][c] = __popc(peers);
         __syncthreads();
+        const int live_warps = min(TO_THREADS / 32, (tiles - t0 + 31) / 32);     // warps that hold tiles
         for (int b = tid; b < TO_BUCKETS; b += TO_THREADS) {
             int run = bucket_base[b];
-            for (int w = 0; w < TO_THREADS / 32; ++w) { const int n = wcnt[w][b]; wcnt[w][b] = run; run += n; }
+            for (int w = 0; w < live_warps; ++w) { const int n = wcnt[w][b]; wcnt[w][b] = run; run += n; }
             bucket_base[b] = run;
         }
         __syncthreads();

@@ -29,3 +29,11 @@ print("tile top | after fetch | after idx_full | after active_groups")
 for i in range(min(len(t5)//4,14)): print(i, t5[4*i:4*i+4])
 print("stage | prod: got_empty_a issued | mma: got_full_a issued+committed")
 for i in range(min(len(prod)//2,36)): print(f"{i:3d} | {prod[2*i]:7d} {prod[2*i+1]:7d} | {mma[2*i]:7d} {mma[2*i+1]:7d}")
+
+sp=t[2][:512*4].reshape(-1,4); sp=sp[sp[:,0]>0]
+if len(sp):
+    s0=sp[:,0].min(); r=(sp-s0)/1000.0
+    half=len(r)//2
+    for name,rr in (("pass 0",r[:half]),("pass 1",r[half:])):
+        d=rr[:,2]-rr[:,1]
+        print(f"{name}: CTAs {len(rr)}  main loop (prologue done -> accumulators done) min {d.min():.1f} median {np.median(d):.1f} max {d.max():.1f} us; exit median {np.median(rr[:,3]):.1f} max {rr[:,3].max():.1f} us")
