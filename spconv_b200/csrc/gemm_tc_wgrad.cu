@@ -21,7 +21,8 @@ constexpr int WG_TILE = 128;
 constexpr int WG_PROD_WARPS = 8;        // 16 tile rows per producer warp
 constexpr int WG_PROD_THREADS = WG_PROD_WARPS * 32;
 constexpr int WG_MMA_WARP = 4 + WG_PROD_WARPS;
-constexpr int WG_THREADS = (WG_MMA_WARP + 1) * 32;   // warps 0-3 epilogue | 4-11 producers | 12 MMA issuer
+constexpr int WG_SCHED_WARP = WG_MMA_WARP + 1;
+constexpr int WG_THREADS = (WG_SCHED_WARP + 1) * 32; // warps 0-3 drain | 4-11 producers | 12 MMA issuer | 13 tile feeder
 constexpr int WG_MAX_STAGES = 6;
 constexpr int WG_SMEM_BUDGET = 200 * 1024;    // operand stages are sized inside this ...
 constexpr int WG_SMEM_MAX = 224 * 1024;       // ... what is left up to here buys deeper index prefetch
@@ -125,6 +126,7 @@ tc_wgrad_kernel(const WgParams p) {
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(acc_done + 1);
     uint32_t *used_smem = tmem_ptr_smem + 1;
     uint32_t *gmask = used_smem + 1;                  // [32][4] offsets covered by each group of this pass
+    uint32_t *slot_info = gmask + 32 * 4;             // [WG_MAX_IDX][8]: {active groups, tile mask[4]} per ring slot
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -172,8 +174,6 @@ tc_wgrad_kernel(const WgParams p) {
     if (warp >= 4 && warp < WG_MMA_WARP) {
         // ================================================= producers
         const int pw = warp - 4;
-        const bool leader = (pw == 0 && lane == 0);
-        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
         int stage = 0; uint32_t phase = 0;
         int64_t nb = 0;                                  // B buffers filled so far
         int nst = 0, ntile = 0;
@@ -197,14 +197,8 @@ tc_wgrad_kernel(const WgParams p) {
             dstd_off[itc] = (chd >> LG_SPAN_D) * (uint32_t)(WG_TILE * SPAN_D) +
                             swizzle_offset((row_in_tile << LG_SPAN_D) + (chd & (uint32_t)(SPAN_D - 1)), SPAN_D);
         }
-        // index-block ring: slot / use count advance together with the tile counters (no modulo)
+        // index-block ring (filled by the feeder warp): slot / use count advance with the tiles
         const int nring = p.idx_bufs;
-        auto fetch_indices = [&](int64_t t, int slot, uint32_t use) {
-            mbar_wait(&idx_empty[slot], (use & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&idx_full[slot], blk_bytes);
-            bulk_copy_g2s(smem_base + idx_off + (uint32_t)slot * p.idx_bytes,
-                          p.tile_table + t * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[slot]);
-        };
         // dout tile (MN-major B operand) of the tile whose index block is idx_s; source rows = block row kv
         auto issue_b = [&](const int32_t *idx_s) {
             const int bb = (int)(nb & 1);
@@ -226,45 +220,32 @@ tc_wgrad_kernel(const WgParams p) {
         auto idx_block = [&](int b) {
             return reinterpret_cast<const int32_t *>(smem + idx_off + (size_t)b * p.idx_bytes);
         };
-        // Software pipeline over tiles: while the x atoms of tile t are being gathered, the index
-        // block of tile t+1 is already in flight, and right after the first stage of tile t its
-        // group set is computed and its dout tile is issued -- nothing but the first x stage sits
-        // on the tile boundary.
+        // Software pipeline over tiles: the feeder warp keeps the ring of index blocks (and each
+        // tile's group set) filled nring-1 tiles ahead; right after the first x stage of tile t
+        // the dout tile of t+1 is issued -- nothing but the first x stage sits on the boundary.
+        auto read_slot = [&](int slot, uint32_t use, uint32_t (&m)[4]) -> uint32_t {
+            mbar_wait(&idx_full[slot], use & 1u);
+            const volatile uint32_t *r = slot_info + slot * 8;
+            m[0] = r[1]; m[1] = r[2]; m[2] = r[3]; m[3] = r[4];
+            return r[0];
+        };
         int64_t tile = chunk;
         int cur_slot = 0; uint32_t cur_use = 0;          // ring position of the tile being gathered
-        int pf_slot = 0; uint32_t pf_use = 0;            // ring position of the next block to fetch
-        int64_t pf_tile = chunk;
-        auto prefetch_one = [&]() {                      // leader only
-            if (pf_tile < num_tiles) {
-                fetch_indices(pf_tile, pf_slot, pf_use);
-                pf_tile += chunks;
-                if (++pf_slot == nring) { pf_slot = 0; ++pf_use; }
-            }
-        };
         uint32_t tm[4] = {0, 0, 0, 0}, tm1[4] = {0, 0, 0, 0};
         uint32_t act = 0;
         if (tile < num_tiles) {
-            if (leader)
-                for (int i = 0; i < nring - 1; ++i) prefetch_one();
-            wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
-            if (tile + chunks < num_tiles) wg_load_tile_mask(p.tile_mask, tile + chunks, p.words, tm1);
-            mbar_wait(&idx_full[0], 0u);
-            act = active_groups(tm, gmask, ng, p.words);
+            act = read_slot(0, 0u, tm);
             if (act) issue_b(idx_block(0));
         }
         for (; tile < num_tiles; tile += chunks) {
             const int64_t next = tile + chunks;
             const bool has_next = next < num_tiles;
-            uint32_t tm2[4] = {0, 0, 0, 0};              // tile masks run two tiles ahead
-            if (next + chunks < num_tiles) wg_load_tile_mask(p.tile_mask, next + chunks, p.words, tm2);
-            if (leader) prefetch_one();                  // block of tile + (nb-1)
             int nxt_slot = cur_slot + 1; uint32_t nxt_use = cur_use;
             if (nxt_slot == nring) { nxt_slot = 0; ++nxt_use; }
             uint32_t act_next = 0;
             bool next_ready = !has_next;
             auto prepare_next = [&]() {
-                mbar_wait(&idx_full[nxt_slot], nxt_use & 1u);
-                act_next = active_groups(tm1, gmask, ng, p.words);
+                act_next = read_slot(nxt_slot, nxt_use, tm1);
                 if (act_next) issue_b(idx_block(nxt_slot));
                 next_ready = true;
             };
@@ -301,9 +282,44 @@ tc_wgrad_kernel(const WgParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&idx_empty[cur_slot]);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { tm[w] = tm1[w]; tm1[w] = tm2[w]; }
+            for (int w = 0; w < 4; ++w) tm[w] = tm1[w];
             act = act_next;
             cur_slot = nxt_slot; cur_use = nxt_use;
+        }
+    } else if (warp == WG_SCHED_WARP) {
+        // ================================================= tile feeder
+        // Per tile of this CTA (static round-robin, so the summation order of dW is fixed): compute
+        // the active groups of this pass from the tile mask, publish them with the mask through
+        // the ring slot, and bulk-copy the tile's index block -- only when the pass has work for
+        // the tile.  Tile masks are fetched 32 tiles at a time, one per lane.
+        const uint32_t blk_bytes = (uint32_t)(p.kv + 1) * 512u;
+        const int nring = p.idx_bufs;
+        int slot = 0; uint32_t use = 0;
+        uint32_t mw[4] = {0, 0, 0, 0};
+        int64_t i = 0;
+        for (int64_t tile = chunk; tile < num_tiles; tile += chunks, ++i) {
+            if ((i & 31) == 0) {
+                const int64_t t = tile + (int64_t)lane * chunks;
+                if (t < num_tiles) wg_load_tile_mask(p.tile_mask, t, p.words, mw);
+            }
+            uint32_t tm[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tm[w] = __shfl_sync(0xffffffffu, mw[w], (int)(i & 31));
+            const uint32_t act = active_groups(tm, gmask, ng, p.words);
+            mbar_wait(&idx_empty[slot], (use & 1u) ^ 1u);
+            if (lane == 0) {
+                uint32_t *r = slot_info + slot * 8;
+                r[0] = act; r[1] = tm[0]; r[2] = tm[1]; r[3] = tm[2]; r[4] = tm[3];
+                if (act) {
+                    mbar_arrive_expect_tx(&idx_full[slot], blk_bytes);
+                    bulk_copy_g2s(smem_base + idx_off + (uint32_t)slot * p.idx_bytes,
+                                  p.tile_table + tile * (int64_t)(p.kv + 1) * 128, blk_bytes, &idx_full[slot]);
+                } else {
+                    mbar_arrive(&idx_full[slot]);
+                }
+            }
+            __syncwarp();
+            if (++slot == nring) { slot = 0; ++use; }
         }
     } else if (warp == WG_MMA_WARP) {
         // ================================================= MMA issuer
