@@ -148,20 +148,6 @@ simt_gather_gemm_kernel(GatherGemmArgs a, SimtEpilogue ep) {
     if (a.mask_out && tid < words) a.mask_out[(int64_t)blockIdx.x * words + tid] = tile_mask[tid];
 }
 
-// SIMT mask_out has S_TM-row granularity; the public contract is 128 rows -> merge 4 tiles
-__global__ void merge_mask_out_kernel(const uint32_t *__restrict__ fine, int64_t fine_tiles, int words, int ratio,
-                                      uint32_t *__restrict__ coarse, int64_t coarse_tiles) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= coarse_tiles * words) return;
-    int64_t t = i / words; int w = (int)(i % words);
-    uint32_t m = 0;
-    for (int j = 0; j < ratio; ++j) {
-        int64_t f = t * ratio + j;
-        if (f < fine_tiles) m |= fine[f * words + w];
-    }
-    coarse[i] = m;
-}
-
 template <typename T>
 static int launch_simt(const GatherGemmArgs &a, const SimtEpilogue &ep, cudaStream_t stream) {
     if (a.rows == 0) return 0;

@@ -40,6 +40,7 @@ struct WgParams {
     int kv, words, c_in;
     float *partial; int64_t partial_stride;
     long long *dbg_ts;           // optional [8][2048] clock64 stamps of CTA (0,0) (SPX_TC_TRACE)
+    int debug;                   // SPX_TC_DEBUG ablation bits (perf triage only): 16 no partial stores, 32 no TMEM loads
 };
 
 __device__ __forceinline__ bool bit_set(const uint32_t (&m)[4], int k) { return (m[k >> 5] >> (k & 31)) & 1u; }
@@ -415,7 +416,7 @@ tc_wgrad_kernel(const WgParams p) {
                 uint32_t v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
-                if (has) {
+                if (has && !(p.debug & 32)) {
                     uint32_t lo[16], hi[16];
                     tmem_ld_32x32b_x16(t_row + (uint32_t)n0, lo);
                     if (cols == 32) tmem_ld_32x32b_x16(t_row + (uint32_t)n0 + 16u, hi);
@@ -423,7 +424,7 @@ tc_wgrad_kernel(const WgParams p) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = cols == 32 ? hi[j] : 0u; }
                 }
-                if (valid) {
+                if (valid && !(p.debug & 16)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < cols) part[((int64_t)(n0 + j) * p.kv + k) * p.c_in + c] = __uint_as_float(v[j]);
@@ -553,6 +554,8 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     {
         const char *trace = getenv("SPX_TC_TRACE");
         pl.p.dbg_ts = trace ? (long long *)strtoull(trace, nullptr, 16) : nullptr;
+        const char *dbg = getenv("SPX_TC_DEBUG");
+        pl.p.debug = dbg ? atoi(dbg) : 0;
     }
     SPX_REQUIRE((size_t)pl.chunks * pl.p.partial_stride * sizeof(float) <= a.workspace_bytes,
                 "tc_wgrad: workspace too small");

@@ -15,7 +15,7 @@ _,_,pf,pb,mf,mb,sf,sb,masks=res
 bw=lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True)
 for _ in range(3): bw()
 ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
-os.environ["SPX_TC_DEBUG"]="0"
+os.environ["SPX_TC_DEBUG"]=os.environ.get("WG_DEBUG","0")
 os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
 bw(); torch.cuda.synchronize()
 t=ts.cpu().numpy(); t0=t[3,0]
