@@ -240,62 +240,83 @@ __global__ void subm_probe_kernel(Table table, Geom g, const int32_t *__restrict
 // 3-D, 3x3x3 (any dilation), 32-bit keys -- the shape of every SubMConv3d in SECOND-style nets.
 // (The generic kernel above exposes one L2 round trip per offset and spends ~150 instructions per
 // probe on generic n-d index arithmetic.)
-// One thread per (voxel, offset): a warp probes ONE kernel offset for 32 consecutive voxels, a block
-// (27 warps) covers all offsets of those voxels.  Compared with a thread that loops over offsets
-// this keeps no per-offset state in registers (full occupancy), has no predicated-off work, and a
-// collision chain only stalls the 32 probes that share its warp.  The warp's hit ballot is the
-// column of mask bits of its offset; thread v < 32 assembles voxel v's mask word from the 27
-// ballots.  Rows of the table are also staged in shared memory for the row-major copy.
-constexpr int K3_VOX = 32;                     // voxels per block; block = 27 * K3_VOX threads
-__global__ void __launch_bounds__(27 * K3_VOX)
+// A warp probes ONE kernel offset for K3_VOX = 128 consecutive voxels (four per lane), a block
+// (27 warps) covers all offsets of those voxels.  The kernel is a chain of dependent L2 round
+// trips (coordinates -> slot -> collision chain -> stores); per-offset state is one key / slot per
+// voxel, so every thread keeps four independent probes in flight at full occupancy, and chains
+// advance in rounds (one extra round trip per round for the whole warp, not per probe).  The
+// warp's hit ballots are the columns of mask bits of its offset; thread v assembles voxel v's mask
+// word from the 27 ballots.  Rows of the table are staged in shared memory for the row-major copy.
+constexpr int K3_VOX = 128;                    // voxels per block; block = 27 warps
+constexpr int K3_PER_LANE = K3_VOX / 32;
+__global__ void __launch_bounds__(27 * 32, 2)
 subm_probe_k3_kernel(Table32 table, Geom g, const int32_t *__restrict__ indices, int64_t N,
                      int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
                      uint32_t *__restrict__ mask, int32_t *__restrict__ row_table) {
-    __shared__ uint32_t hit_col[27];
+    __shared__ uint32_t hit_col[27][K3_PER_LANE];
     __shared__ int32_t row_stage[K3_VOX][27];     // odd row stride: conflict-free both ways
-    const int lo = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int k = threadIdx.x >> 5;               // warp-uniform kernel offset, k = (rz*3 + ry)*3 + rx
     const int rz = k / 9, ry = (k / 3) % 3, rx = k % 3;
     const int64_t vbase = blockIdx.x * (int64_t)K3_VOX;
-    const int64_t o = vbase + lo;
-    int32_t found = -1;
-    if (o < N) {
-        const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + o);    // (b, z, y, x)
-        const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
-        // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
-        const int qz = c.y + (rz - 1) * g.dilation[0];
-        const int qy = c.z + (ry - 1) * g.dilation[1];
-        const int qx = c.w + (rx - 1) * g.dilation[2];
-        const bool valid = c.x >= 0 && c.x < g.batch && qz >= 0 && qz < D0 && qy >= 0 && qy < D1 && qx >= 0 && qx < D2;
-        if (k == 13) {
-            found = (int32_t)o;                       // centre: identity
-        } else if (valid) {
-            const uint32_t key = (uint32_t)(((c.x * D0 + qz) * D1 + qy) * D2 + qx);
-            uint32_t h = mix32(key) & table.cap_mask;
-            unsigned long long cur = __ldg(&table.slots[h]);
-            while (cur != Table32::EMPTY) {           // collision chain (short at load factor <= 0.25)
-                if ((uint32_t)(cur >> 32) == key) { found = (int32_t)(uint32_t)cur; break; }
-                h = (h + 1) & table.cap_mask;
-                cur = __ldg(&table.slots[h]);
-            }
-        }
-        pair_fwd[(int64_t)k * N + o] = found;
-        if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
+    const int D0 = g.in_dims[0], D1 = g.in_dims[1], D2 = g.in_dims[2];
+    // q_a = c_a + (r_a - 1) * dil_a   (pad = dil for ksize 3), r_a in {0,1,2}
+    const int oz = (rz - 1) * g.dilation[0], oy = (ry - 1) * g.dilation[1], ox = (rx - 1) * g.dilation[2];
+    int4 c[K3_PER_LANE];
+#pragma unroll
+    for (int j = 0; j < K3_PER_LANE; ++j) {
+        const int64_t o = vbase + j * 32 + lane;
+        c[j] = o < N ? __ldg(reinterpret_cast<const int4 *>(indices) + o) : make_int4(-1, 0, 0, 0);
     }
-    const uint32_t hits = __ballot_sync(0xffffffffu, found >= 0);
-    if (lo == 0) hit_col[k] = hits;
-    row_stage[lo][k] = found;
+    uint32_t key[K3_PER_LANE], h[K3_PER_LANE];
+    unsigned long long cur[K3_PER_LANE];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int j = 0; j < K3_PER_LANE; ++j) {
+        const int qz = c[j].y + oz, qy = c[j].z + oy, qx = c[j].w + ox;
+        const bool valid = k != 13 && c[j].x >= 0 && c[j].x < g.batch && qz >= 0 && qz < D0 && qy >= 0 && qy < D1 &&
+                           qx >= 0 && qx < D2;
+        key[j] = (uint32_t)(((c[j].x * D0 + qz) * D1 + qy) * D2 + qx);
+        h[j] = mix32(key[j]) & table.cap_mask;
+        cur[j] = valid ? __ldg(&table.slots[h[j]]) : Table32::EMPTY;
+    }
+#pragma unroll
+    for (int j = 0; j < K3_PER_LANE; ++j)
+        if (cur[j] != Table32::EMPTY && (uint32_t)(cur[j] >> 32) != key[j]) pending |= 1u << j;
+    while (pending) {                             // collision chains (short at load factor <= 0.25)
+#pragma unroll
+        for (int j = 0; j < K3_PER_LANE; ++j)
+            if (pending & (1u << j)) { h[j] = (h[j] + 1) & table.cap_mask; cur[j] = __ldg(&table.slots[h[j]]); }
+#pragma unroll
+        for (int j = 0; j < K3_PER_LANE; ++j)
+            if ((pending & (1u << j)) && (cur[j] == Table32::EMPTY || (uint32_t)(cur[j] >> 32) == key[j]))
+                pending &= ~(1u << j);
+    }
+#pragma unroll
+    for (int j = 0; j < K3_PER_LANE; ++j) {
+        const int64_t o = vbase + j * 32 + lane;
+        int32_t found = cur[j] != Table32::EMPTY ? (int32_t)(uint32_t)cur[j] : -1;
+        if (k == 13 && o < N) found = (int32_t)o;     // centre: identity
+        if (o < N) {
+            pair_fwd[(int64_t)k * N + o] = found;
+            if (pair_bwd) pair_bwd[(int64_t)(26 - k) * N + o] = found;
+        }
+        const uint32_t hits = __ballot_sync(0xffffffffu, found >= 0);
+        if (lane == 0) hit_col[k][j] = hits;
+        row_stage[j * 32 + lane][k] = found;
+    }
     __syncthreads();
-    if (mask && k == 0 && o < N) {
+    if (mask && threadIdx.x < K3_VOX && vbase + threadIdx.x < N) {
+        const int v = threadIdx.x;
         uint32_t m = 0;
 #pragma unroll
-        for (int kk = 0; kk < 27; ++kk) m |= ((hit_col[kk] >> lo) & 1u) << kk;
-        mask[o] = m;
+        for (int kk = 0; kk < 27; ++kk) m |= ((hit_col[kk][v >> 5] >> (v & 31)) & 1u) << kk;
+        mask[vbase + v] = m;
     }
     if (row_table) {
         // row-major copy [N][32] (one 128-byte line per voxel, -1 padded) for spx_build_tile_table:
         // the permuted re-read then costs 4 sectors per row instead of one per (row, offset)
-        for (int e = threadIdx.x; e < K3_VOX * 32; e += 27 * K3_VOX) {
+        for (int e = threadIdx.x; e < K3_VOX * 32; e += 27 * 32) {
             const int v = e >> 5, kk = e & 31;
             if (vbase + v < N) row_table[(vbase + v) * 32 + kk] = kk < 27 ? row_stage[v][kk] : -1;
         }
@@ -864,8 +885,8 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
         subm_insert_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("subm_insert_kernel");
         if (subm_k3_path(gg)) {
-            subm_probe_k3_kernel<<<(unsigned)div_up64(N, K3_VOX), 27 * K3_VOX, 0, stream>>>(t, gg, indices, N, pair_fwd,
-                                                                                            pair_bwd, mask, row_table);
+            subm_probe_k3_kernel<<<(unsigned)div_up64(N, K3_VOX), 27 * 32, 0, stream>>>(t, gg, indices, N, pair_fwd,
+                                                                                        pair_bwd, mask, row_table);
         } else {
             SPX_REQUIRE(row_table == nullptr, "row_table is only produced when spx_subm_row_table_supported()");
             subm_probe_kernel<<<nblk, T, 0, stream>>>(t, gg, indices, N, pair_fwd, pair_bwd, mask, words);
