@@ -459,11 +459,13 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
                                                     _ptr(dfilters), ws.data_ptr(), ws.numel(),
                                                     _stream()), "implicit_gemm_wgrad")
 
-    if timer.enable or not (n_in and n_out):
-        run_dgrad()                 # profiling regions stay one kernel each
+    if timer.enable or not (n_in and n_out) or not torch.cuda.is_current_stream_capturing():
+        # eager launches are host-bound (and an eager fork/join per call measured slower, not
+        # faster); profiling regions stay one kernel each
+        run_dgrad()
         run_wgrad()
         return din, dfilters
-    # The two gradients are independent.  The weight-gradient kernel (one CTA per SM, statically
+    # Under CUDA-graph capture the two independent gradients become parallel branches.  The weight-gradient kernel (one CTA per SM, statically
     # assigned tiles) has a long tail -- its CTAs finish over a ~15 us window -- so it goes first on
     # the caller's stream and the dynamically scheduled input-gradient kernel is queued on a forked
     # stream: its CTAs fill the SMs the weight gradient has already left.  Joined before returning.
