@@ -280,3 +280,62 @@ def test_dynamic_scheduler_leaves_state_clean_and_is_repeatable(cuda_dev):
     assert (table[-64:] == 0).all(), "scheduler scratch must be zero between launches"
     for o, d in zip(outs[1:], dins[1:]):
         assert torch.equal(o, outs[0]) and torch.equal(d, dins[0])
+
+
+@pytest.mark.parametrize("workload", ["cfg2_subm_fp16_100k", "cfg4_conv_bf16_300k"])
+def test_full_size_configs_against_torch_fp32_reference(workload, cuda_dev):
+    """BASELINE.json configs[1] and configs[3] at FULL size.  The oracle's numpy loops need minutes
+    there, so the check is a plain PyTorch fp32 restatement of the same sum on the GPU
+    (out[o] = sum_k x[pair[k][o]] @ W[:, k, :]^T, spconv/csrc/sparse/convops.py:1606-1633 and its
+    two gradients, :1831-1860), driven by the rulebook this engine built -- that rulebook is compared
+    bit for bit with the oracle at the same size in tests/test_rulebook_gpu.py -- plus two
+    size-independent properties: exact homogeneity under a power-of-two scale, and gradients that
+    are linear in dout."""
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch import ops
+    if workload.startswith("cfg2"):
+        shape, n, C, K, tdt, subm, st, tol = [41, 1600, 1408], 100_000, 64, 64, torch.float16, True, 1, 2e-3
+    else:
+        shape, n, C, K, tdt, subm, st, tol = [41, 1440, 1440], 300_000, 64, 128, torch.bfloat16, False, 2, 1e-2
+    rng = np.random.default_rng(2025)
+    inds = torch.from_numpy(surface_cloud(rng, shape, n)).to(cuda_dev)
+    res = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [st] * 3,
+                                             [1] * 3, [1] * 3, [0] * 3, subm, False, is_train=True)
+    out_inds, _, pf, pb, mf, mb, sf, sb, masks = res
+    m = out_inds.shape[0]
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    x = (torch.rand((n, C), device=cuda_dev, generator=g) - 0.5).to(tdt)
+    w = ((torch.rand((K, 3, 3, 3, C), device=cuda_dev, generator=g) - 0.5) * 0.25).to(tdt)
+    dout = ((torch.rand((m, K), device=cuda_dev, generator=g) - 0.5) * 0.4).to(tdt)
+    out, mask_out, mw = ops.implicit_gemm(x, w, pf, mf, sf, m, masks, True, subm)
+    din, dw = ops.implicit_gemm_backward(x, w, dout, pf, pb, mf, mb, sf, sb, mask_out, masks, mw, subm)
+
+    xf, wf, df = x.float(), w.float().reshape(K, 27, C), dout.float()
+    ref_out = torch.zeros((m, K), device=cuda_dev)
+    ref_din = torch.zeros((n, C), device=cuda_dev)
+    ref_dw = torch.zeros((K, 27, C), device=cuda_dev)
+    for k in range(27):
+        src = pf[k].long()
+        hit = src >= 0
+        rows = hit.nonzero(as_tuple=True)[0]
+        xin = xf[src[rows]]
+        ref_out[rows] += xin @ wf[:, k, :].t()
+        ref_dw[:, k, :] = df[rows].t() @ xin
+        ref_din.index_add_(0, src[rows], df[rows] @ wf[:, k, :])
+
+    def rel(a, b):
+        return float((a.float() - b).norm() / b.norm().clamp_min(1e-20))
+    assert rel(out, ref_out) <= tol, f"forward rel-L2 {rel(out, ref_out):.3e}"
+    assert rel(din, ref_din) <= tol, f"dgrad rel-L2 {rel(din, ref_din):.3e}"
+    assert rel(dw.reshape(K, 27, C), ref_dw) <= tol, f"wgrad rel-L2 {rel(dw.reshape(K, 27, C), ref_dw):.3e}"
+    # homogeneity: scaling the input by 2 scales the output by exactly 2 (fp32 accumulation, no overflow)
+    # (compared where the 1x result is a normal number of the output type: a subnormal 1x value is
+    # rounded on a coarser grid than its 2x counterpart)
+    out2, _, _ = ops.implicit_gemm(x * 2, w, pf, mf, sf, m, masks, True, subm)
+    big = out.float().abs() >= 1e-3
+    assert torch.equal(out2.float()[big], (out.float() * 2)[big])
+    # gradients are linear in dout
+    din2, dw2 = ops.implicit_gemm_backward(x, w, dout * 2, pf, pb, mf, mb, sf, sb, mask_out, masks, mw, subm)
+    big = din.float().abs() >= 1e-3
+    assert torch.equal(din2.float()[big], (din.float() * 2)[big])
+    assert rel(dw2.float(), dw.float() * 2) <= 1e-3
