@@ -1,15 +1,20 @@
 // tcgen05 / TMEM / TMA masked implicit GEMM: forward and input-gradient (and int8 forward).
 //
-// One persistent CTA per SM walks 128-row output tiles (rows in mask_argsort order).  Per tile
-// the gather indices arrive as ONE bulk async copy (cp.async.bulk) of the tile's block of the
-// tile table (spx_build_tile_table), prefetched a tile ahead.  For each kernel offset whose bit
-// is set in the tile's OR-mask:
-//   * 4 producer warps gather the 128 input rows into a swizzled K-major shared-memory tile with
+// Persistent CTAs (two per SM when the tile fits 104 KB of shared memory and 256 TMEM columns)
+// work on 128-row output tiles (rows in mask_argsort order).  Tiles are handed out DYNAMICALLY:
+// a scheduler warp draws tickets from an atomic counter and takes tiles from the schedule records
+// behind the tile table (heaviest first = LPT list scheduling, see gemm.cuh / rulebook.cu); the
+// tile's gather indices arrive as ONE bulk async copy (cp.async.bulk) of its block of the tile
+// table (spx_build_tile_table), one tile ahead.  For each kernel offset whose bit is set in the
+// tile's OR-mask:
+//   * 8 producer warps gather the 128 input rows into a swizzled K-major shared-memory tile with
 //     16-byte cp.async (zero-fill for "-1 = no neighbour"); all per-lane addressing is hoisted
-//     out of the pipeline (compile-time chunk count CPR), ~6 instructions per 16-byte copy;
-//   * one lane TMA-loads that offset's KRSC weight slice W[:, k, :] (a strided 2-D box);
-//   * one lane issues tcgen05.mma (M = 128, N = out channels, K = 32 bytes per instruction)
-//     accumulating the whole offset sum in TMEM;
+//     out of the pipeline (compile-time chunk count CPR), the row indices of the next offset are
+//     read before the wait for the next free stage;
+//   * the TMA warp loads that offset's KRSC weight slice W[:, k, :] (a strided 2-D box);
+//   * the MMA warp issues tcgen05.mma (M = 128, N = out channels, K = 32 bytes per instruction;
+//     warp-uniform descriptor arithmetic, an elected lane fires) accumulating the whole offset sum
+//     in TMEM;
 // and 4 epilogue warps drain the previous tile's accumulator (tcgen05.ld -> bias/act ->
 // vectorised row stores) while the next tile is being multiplied (two TMEM accumulators).
 //

@@ -12,6 +12,10 @@
 //   * each CTA finally dumps its TMEM to an fp32 partial buffer and a small second kernel sums
 //     the partials in a fixed order (deterministic; the reference's split-K does the same
 //     with fp32 workspaces, spconv/csrc/sparse/convops.py:1236-1243, :2421-2436).
+// Roles: warps 0-3 drain only, 4-11 gather producers (16-byte cp.async, 16 tile rows per warp;
+// they join the drain at the end), 12 MMA issuer, 13 tile feeder (index-block ring + per-tile
+// group sets).  Tiles are assigned statically (chunk, chunk + chunks, ...) so the summation
+// order of dW -- and with it the result -- is reproducible bit for bit.
 #include "gemm.cuh"
 #include <stdlib.h>
 
