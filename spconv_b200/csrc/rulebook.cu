@@ -397,6 +397,79 @@ __global__ void conv_insert_kernel(Table table, Geom g, const int32_t *__restric
     }
 }
 
+// 3-D, 3x3x3, non-transposed: one thread per INPUT voxel walks the 27 offsets.  The per-axis output
+// coordinates of the three taps are computed once (9 divisions-by-stride instead of 81), and with a
+// stride > 1 most (axis, tap) pairs fail the divisibility test, so only the surviving combinations
+// (3.4 of 27 on average at stride 2) reach the hash table.  The grid-(N, kv) kernels above re-read
+// the coordinates 27 times and spend a thread per rejected combination.
+struct Axis3 { int o[3]; };
+__device__ __forceinline__ Axis3 axis_taps3(int c, int pad, int dil, int stride, int odim) {
+    Axis3 a;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { int o; a.o[r] = axis_out(c, pad, r, dil, stride, odim, o) ? o : -1; }
+    return a;
+}
+
+template <typename Table>
+__global__ void conv_insert_k3_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+    if (c.x < 0 || c.x >= g.batch) return;
+    const Axis3 az = axis_taps3(c.y, g.padding[0], g.dilation[0], g.stride[0], g.out_dims[0]);
+    const Axis3 ay = axis_taps3(c.z, g.padding[1], g.dilation[1], g.stride[1], g.out_dims[1]);
+    const Axis3 ax = axis_taps3(c.w, g.padding[2], g.dilation[2], g.stride[2], g.out_dims[2]);
+#pragma unroll
+    for (int r0 = 0; r0 < 3; ++r0) {
+        if (az.o[r0] < 0) continue;
+        const int64_t kz = (int64_t)c.x * g.out_dims[0] + az.o[r0];
+#pragma unroll
+        for (int r1 = 0; r1 < 3; ++r1) {
+            if (ay.o[r1] < 0) continue;
+            const int64_t kzy = kz * g.out_dims[1] + ay.o[r1];
+#pragma unroll
+            for (int r2 = 0; r2 < 3; ++r2) {
+                if (ax.o[r2] < 0) continue;
+                const int k = (r0 * 3 + r1) * 3 + r2;
+                table.insert_min(kzy * g.out_dims[2] + ax.o[r2], (int32_t)((int64_t)k * N + i));
+            }
+        }
+    }
+}
+
+// pair_bwd[k][i] = output of (input i, offset k) or -1 (every element written, coalesced over i);
+// pair_fwd[k][o] = i scattered
+template <typename Table>
+__global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N, int64_t M,
+                                     int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+    const bool bok = c.x >= 0 && c.x < g.batch;
+    const Axis3 az = axis_taps3(c.y, g.padding[0], g.dilation[0], g.stride[0], g.out_dims[0]);
+    const Axis3 ay = axis_taps3(c.z, g.padding[1], g.dilation[1], g.stride[1], g.out_dims[1]);
+    const Axis3 ax = axis_taps3(c.w, g.padding[2], g.dilation[2], g.stride[2], g.out_dims[2]);
+#pragma unroll
+    for (int r0 = 0; r0 < 3; ++r0) {
+#pragma unroll
+        for (int r1 = 0; r1 < 3; ++r1) {
+#pragma unroll
+            for (int r2 = 0; r2 < 3; ++r2) {
+                const int k = (r0 * 3 + r1) * 3 + r2;
+                int32_t out = -1;
+                if (bok && az.o[r0] >= 0 && ay.o[r1] >= 0 && ax.o[r2] >= 0) {
+                    const int64_t key = (((int64_t)c.x * g.out_dims[0] + az.o[r0]) * g.out_dims[1] + ay.o[r1]) *
+                                            g.out_dims[2] + ax.o[r2];
+                    int32_t v;
+                    if (table.find_slot(key, v) >= 0) out = v;
+                }
+                pair_bwd[(int64_t)k * N + i] = out;
+                if (out >= 0) pair_fwd[(int64_t)k * M + out] = (int32_t)i;
+            }
+        }
+    }
+}
+
 // compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next).
 // The table is sized for the worst-case output count, so most of it is empty: every thread scans
 // COLLECT_ITEMS slots and a block reserves its output range with ONE atomic (a single global
@@ -948,12 +1021,14 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
     const int T = 128;
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
     const bool fast3 = gg.ndim == 3 && !gg.transposed;
+    const bool k3 = fast3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
     SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
     SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
     unsigned cblk = (unsigned)div_up64(w.L.capacity, COLLECT_THREADS * COLLECT_ITEMS);
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
-        if (fast3) conv_insert_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
+        if (k3) conv_insert_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N);
+        else if (fast3) conv_insert_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
         else conv_insert_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("conv_insert_kernel");
         conv_collect_kernel<<<cblk, COLLECT_THREADS, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
@@ -961,7 +1036,8 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
     } else {
         SPX_CHECK_CUDA(cudaMemsetAsync(w.tvals, 0x7F, (size_t)w.L.capacity * 4, stream));
         Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
-        if (fast3) conv_insert_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
+        if (k3) conv_insert_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N);
+        else if (fast3) conv_insert_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N);
         else conv_insert_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N);
         SPX_CHECK_LAUNCH("conv_insert_kernel");
         conv_collect_kernel<<<cblk, COLLECT_THREADS, 0, stream>>>(t, w.L.capacity, w.payload, w.slot, w.counter);
@@ -997,19 +1073,22 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
     const int T = 128;
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
     const bool fast3 = gg.ndim == 3 && !gg.transposed;
+    const bool k3 = fast3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
     SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        else if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     } else {
         Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        else if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     }
