@@ -438,10 +438,11 @@ __global__ void conv_insert_k3_kernel(Table table, Geom g, const int32_t *__rest
 }
 
 // pair_bwd[k][i] = output of (input i, offset k) or -1 (every element written, coalesced over i);
-// pair_fwd[k][o] = i scattered
+// pair_fwd[k][o] = i scattered; mask_bwd[i] (optional) = bits of the offsets that hit an output
 template <typename Table>
 __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N, int64_t M,
-                                     int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd) {
+                                     int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
+                                     uint32_t *__restrict__ mask_bwd) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
@@ -449,6 +450,7 @@ __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restr
     const Axis3 az = axis_taps3(c.y, g.padding[0], g.dilation[0], g.stride[0], g.out_dims[0]);
     const Axis3 ay = axis_taps3(c.z, g.padding[1], g.dilation[1], g.stride[1], g.out_dims[1]);
     const Axis3 ax = axis_taps3(c.w, g.padding[2], g.dilation[2], g.stride[2], g.out_dims[2]);
+    uint32_t mword = 0;
 #pragma unroll
     for (int r0 = 0; r0 < 3; ++r0) {
 #pragma unroll
@@ -464,10 +466,11 @@ __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restr
                     if (table.find_slot(key, v) >= 0) out = v;
                 }
                 pair_bwd[(int64_t)k * N + i] = out;
-                if (out >= 0) pair_fwd[(int64_t)k * M + out] = (int32_t)i;
+                if (out >= 0) { pair_fwd[(int64_t)k * M + out] = (int32_t)i; mword |= 1u << k; }
             }
         }
     }
+    if (mask_bwd) mask_bwd[i] = mword;
 }
 
 // compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next).
@@ -1079,7 +1082,7 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
         Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
         else if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
@@ -1087,7 +1090,7 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
         Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
         conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
         else if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
@@ -1096,7 +1099,7 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
         table_mask_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(pair_fwd, M, gg.kv, words, mask_fwd);
         SPX_CHECK_LAUNCH("table_mask_kernel");
     }
-    if (mask_bwd) {
+    if (mask_bwd && !k3) {                      // the 3x3x3 pairs kernel has already written it
         table_mask_kernel<<<(unsigned)div_up64(N, 256), 256, 0, stream>>>(pair_bwd, N, gg.kv, words, mask_bwd);
         SPX_CHECK_LAUNCH("table_mask_kernel");
     }
