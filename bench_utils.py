@@ -141,3 +141,32 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------- BASELINE.json configs[2]
+# SECOND-style 6-layer sparse encoder (closest reference pattern
+# /root/reference/test/fake_train.py:52-99): (kind, C_in, C_out, indice_key)
+ENCODER6_LAYERS = [
+    ("subm", 16, 16, "subm1"),
+    ("subm", 16, 16, "subm1"),       # shares the rulebook of the layer above (indice_key reuse)
+    ("conv", 16, 32, "down1"),       # 3x3x3, stride 2, padding 1
+    ("subm", 32, 32, "subm2"),
+    ("conv", 32, 64, "down2"),
+    ("conv", 64, 128, "down3"),
+]
+
+
+def make_encoder6(spconv, algo=None, bias: bool = False, relu: bool = False):
+    """The six conv layers as a list of modules (the caller chains them, so tests can look at every
+    intermediate tensor); ``relu=True`` interleaves ``torch.nn.ReLU`` like SECOND does."""
+    import torch
+    layers = []
+    for kind, c_in, c_out, key in ENCODER6_LAYERS:
+        if kind == "subm":
+            layers.append(spconv.SubMConv3d(c_in, c_out, 3, padding=1, bias=bias, indice_key=key, algo=algo))
+        else:
+            layers.append(spconv.SparseConv3d(c_in, c_out, 3, stride=2, padding=1, bias=bias, indice_key=key,
+                                              algo=algo))
+        if relu:
+            layers.append(torch.nn.ReLU())
+    return layers

@@ -245,6 +245,18 @@ int spx_implicit_gemm_fwd_int8(const spx_gemm_desc *d, const int8_t *features,
 int spx_last_kernel_family(void);
 /* number of kernel launches issued by this library on the calling thread since the last reset */
 int64_t spx_launch_count(int reset);
+/*
+ * Test / perf-triage switches (never needed for correct operation; the reference's counterpart is
+ * the SPCONV_DEBUG_* environment, spconv/constants.py:100-125).
+ *   force_family: -1 keep, 0 automatic, 1 generic FMA kernels, 2 tcgen05 kernels (error if the
+ *                 shape does not tile) -- the start-up value comes from SPX_FORCE_SIMT / SPX_FORCE_TC,
+ *                 read once when the library is loaded;
+ *   tc_ctas:      0 keep, 1 or 2 resident CTAs per SM for the forward / dgrad kernel;
+ *   debug_bits:   ablation mask of the tcgen05 kernels (results are wrong by construction when set);
+ *   trace_buf:    NULL or a DEVICE buffer of at least 8*2048 int64 that receives clock stamps.
+ */
+int spx_debug_configure(int force_family, int tc_ctas, int debug_bits, void *trace_buf,
+                        size_t trace_bytes);
 
 #ifdef __cplusplus
 }

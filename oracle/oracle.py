@@ -2,10 +2,17 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this module; the product package
-(``spconv_b200``) never does.  Parity status is "unpinned for pair ORDER" in the
-reference's own tests (see the header of ``spconv_oracle.c``); rulebook CONTENT and the
-conv arithmetic are pinned by the reference's dense-convolution equivalence test, which
-``tests/test_oracle.py`` reruns on CPU.
+(``spconv_b200``) never does.
+
+Parity status: **pinned to the reference itself.**  ``make_ref.py`` extracts the reference's own
+CPU rulebook and gather/scatter C++ from /root/reference and compiles it into
+``oracle/_ref/libspconv_ref.so``; ``tests/test_oracle_ref.py`` holds the C restatement
+(``spconv_oracle.c``) to it bit for bit (pair ORDER included).  The conv loops below follow
+``convops.py:1534-1633,1769-1860`` step by step -- ``GatherCPU::gather`` -> ``torch.mm`` ->
+``GatherCPU::scatter_add`` with the reference's gather/scatter code when ``_ref`` is built -- and
+are additionally pinned by the reference's dense-convolution equivalence test
+(``tests/test_oracle.py``).  Unpinnable (no reference implementation exists): bf16, and the
+implicit-GEMM tables, which the reference only builds on the GPU (derived per SURVEY A.5).
 
 What is restated (paths relative to /root/reference):
 
@@ -32,7 +39,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "spconv_oracle.c")
 _LIB = os.path.join(_HERE, "_build", "libspconv_oracle.so")
+_REF_LIB = os.path.join(_HERE, "_ref", "libspconv_ref.so")
 _lib: Optional[ctypes.CDLL] = None
+_ref: Optional[ctypes.CDLL] = None
+_ref_tried = False
 
 
 def build(force: bool = False) -> str:
@@ -59,6 +69,37 @@ def _load() -> ctypes.CDLL:
         _lib.orc_subm_rulebook.restype = ctypes.c_int
         _lib.orc_conv_rulebook.restype = ctypes.c_int
     return _lib
+
+
+def build_ref(force: bool = False) -> Optional[str]:
+    """Compile ``oracle/_ref/libspconv_ref.so`` -- the reference's OWN CPU rulebook and
+    gather/scatter code, extracted from /root/reference by ``oracle/make_ref.py``.  Returns the
+    path, or None when neither the reference tree nor a prebuilt library is present."""
+    from . import make_ref
+    return make_ref.build(force=force)
+
+
+def ref_lib() -> Optional[ctypes.CDLL]:
+    """The compiled reference code (``oracle/_ref``) or None.  On the GPU box /root/reference does
+    not exist; the library built here travels with the snapshot."""
+    global _ref, _ref_tried
+    if _ref is None and not _ref_tried:
+        _ref_tried = True
+        path = None
+        try:
+            path = build_ref()
+        except Exception:
+            path = _REF_LIB if os.path.exists(_REF_LIB) else None
+        if path and os.path.exists(path):
+            _ref = ctypes.CDLL(path)
+            _ref.ref_subm_rulebook.restype = ctypes.c_int
+            _ref.ref_conv_rulebook.restype = ctypes.c_int
+            _ref.ref_num_threads.restype = ctypes.c_int
+    return _ref
+
+
+def have_ref() -> bool:
+    return ref_lib() is not None
 
 
 def _iarr(v: Sequence[int]):
@@ -94,14 +135,23 @@ def get_deconv_output_size(input_size, kernel_size, stride, padding, dilation,
 def get_indice_pairs(indices: np.ndarray, batch_size: int, spatial_shape: Sequence[int],
                      ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
                      dilation: Sequence[int], out_padding: Sequence[int], subm: bool = False,
-                     transpose: bool = False
+                     transpose: bool = False, impl: str = "port"
                      ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Native rulebook in the reference's CPU order.
 
     Returns ``(out_inds [M, ndim+1], pairs [2, kv, N], indice_num_per_loc [kv])`` exactly
     as ``ops.get_indice_pairs`` does on a CPU tensor (``ops.py:132-170``).
+    ``impl="port"``: the C restatement (``spconv_oracle.c``); ``impl="ref"``: the reference's own
+    C++ (``oracle/_ref``, see ``make_ref.py``) -- ``tests/test_oracle_ref.py`` pins one to the other.
     """
-    lib = _load()
+    if impl == "ref":
+        lib = ref_lib()
+        if lib is None:
+            raise RuntimeError("oracle/_ref is not built (needs /root/reference or a prebuilt library)")
+        f_subm, f_conv = lib.ref_subm_rulebook, lib.ref_conv_rulebook
+    else:
+        lib = _load()
+        f_subm, f_conv = lib.orc_subm_rulebook, lib.orc_conv_rulebook
     indices = np.ascontiguousarray(indices, dtype=np.int32)
     n, ndim = indices.shape[0], indices.shape[1] - 1
     kv = int(np.prod(ksize))
@@ -119,18 +169,18 @@ def get_indice_pairs(indices: np.ndarray, batch_size: int, spatial_shape: Sequen
     pairs = np.full((2, kv, n), -1, dtype=np.int32)
     num = np.zeros((kv,), dtype=np.int32)
     if subm:
-        ret = lib.orc_subm_rulebook(_ptr(indices), n, ndim, int(batch_size), _iarr(spatial_shape),
-                                    _iarr(ksize), _iarr(dilation), _ptr(pairs), _ptr(num))
+        ret = f_subm(_ptr(indices), n, ndim, int(batch_size), _iarr(spatial_shape),
+                     _iarr(ksize), _iarr(dilation), _ptr(pairs), _ptr(num))
         if ret == -2:
             raise RuntimeError("subm only support odd ksize")
         if ret < 0:
             raise RuntimeError(f"oracle subm rulebook failed ({ret})")
         return indices, pairs, num
     out_inds = np.empty((max(kv * n, 1), ndim + 1), dtype=np.int32)
-    num_act = lib.orc_conv_rulebook(_ptr(indices), n, ndim, int(batch_size), _iarr(out_shape),
-                                    _iarr(spatial_shape), _iarr(ksize), _iarr(stride),
-                                    _iarr(padding), _iarr(dilation), int(bool(transpose)),
-                                    _ptr(pairs), _ptr(out_inds), _ptr(num))
+    num_act = f_conv(_ptr(indices), n, ndim, int(batch_size), _iarr(out_shape),
+                     _iarr(spatial_shape), _iarr(ksize), _iarr(stride),
+                     _iarr(padding), _iarr(dilation), int(bool(transpose)),
+                     _ptr(pairs), _ptr(out_inds), _ptr(num))
     if num_act < 0:
         raise RuntimeError(f"oracle conv rulebook failed ({num_act})")
     if num_act == 0:
@@ -197,6 +247,44 @@ def implicit_gemm_tables(pairs: np.ndarray, num: np.ndarray, n_in: int, n_out: i
     }
 
 
+def _mm(a: np.ndarray, b: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """The reference's mm callback is ``torch.mm`` on the host BLAS (``cppcore.py:232-348``)."""
+    try:
+        import torch
+    except Exception:                                   # pragma: no cover
+        return np.matmul(a, b, out=out)
+    if out is None:
+        return torch.mm(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b))).numpy()
+    torch.mm(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b)),
+             out=torch.from_numpy(out))
+    return out
+
+
+def gather_rows(buf: np.ndarray, src: np.ndarray, inds: np.ndarray) -> None:
+    """``GatherCPU::gather`` (``gather.py:30-56``): buf[i] = src[inds[i]].  Runs the reference's
+    own code when ``oracle/_ref`` is built, else its C restatement."""
+    n, c = int(inds.shape[0]), int(src.shape[1])
+    assert buf.dtype == np.float32 and src.dtype == np.float32 and inds.dtype == np.int32
+    assert buf.flags.c_contiguous and src.flags.c_contiguous and inds.flags.c_contiguous
+    r = ref_lib()
+    if r is not None:
+        r.ref_gather_f32(_ptr(buf), _ptr(src), _ptr(inds), n, c, int(src.shape[0]))
+    else:
+        _load().orc_gather_f32(_ptr(buf), _ptr(src), _ptr(inds), n, c)
+
+
+def scatter_add_rows(dst: np.ndarray, buf: np.ndarray, inds: np.ndarray) -> None:
+    """``GatherCPU::scatter_add`` (``gather.py:58-86``): dst[inds[i]] += buf[i]."""
+    n, c = int(inds.shape[0]), int(dst.shape[1])
+    assert dst.dtype == np.float32 and buf.dtype == np.float32 and inds.dtype == np.int32
+    assert dst.flags.c_contiguous and buf.flags.c_contiguous and inds.flags.c_contiguous
+    r = ref_lib()
+    if r is not None:
+        r.ref_scatter_add_f32(_ptr(dst), _ptr(buf), _ptr(inds), n, c, int(dst.shape[0]))
+    else:
+        _load().orc_scatter_add_f32(_ptr(dst), _ptr(buf), _ptr(inds), n, c)
+
+
 def indice_conv(features: np.ndarray, filters: np.ndarray, pairs: np.ndarray, num: np.ndarray,
                 num_activate_out: int, inverse: bool = False, subm: bool = False,
                 bias: Optional[np.ndarray] = None, act: Optional[str] = None,
@@ -206,24 +294,28 @@ def indice_conv(features: np.ndarray, filters: np.ndarray, pairs: np.ndarray, nu
     ``filters`` is KRSC ``[K, *ksize, C]``; it is viewed ``[K, kv, C]`` and offset ``k`` uses
     ``W_k = filters[:, k, :]`` with ``out[pair_out] += x[pair_in] @ W_k^T``.
     """
-    x = np.asarray(features, dtype=np.float32)
+    x = np.ascontiguousarray(features, dtype=np.float32)
     K, C = filters.shape[0], filters.shape[-1]
-    w = np.asarray(filters, dtype=np.float32).reshape(K, -1, C)
+    w = np.ascontiguousarray(filters, dtype=np.float32).reshape(K, -1, C)
     kv = w.shape[1]
     cnt = _pair_counts(num, kv, x.shape[0], subm)
     if subm:
-        out = x @ w[:, kv // 2].T                     # cppcore.py:244-246
+        out = np.ascontiguousarray(_mm(x, w[:, kv // 2].T))       # cppcore.py:244-246
     else:
-        out = np.zeros((num_activate_out, K), dtype=np.float32)
+        out = np.zeros((num_activate_out, K), dtype=np.float32)   # convops.py:1567-1568
     pin, pout = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])  # convops.py:1604-1605
-    for k in range(kv):
+    maxnhot = int(max([cnt[k] for k in range(kv) if not (subm and k == kv // 2)] + [0]))
+    inp_buffer = np.empty((max(maxnhot, 1), C), dtype=np.float32)  # AllocKeys.InpBuffer, :1608
+    out_buffer = np.empty((max(maxnhot, 1), K), dtype=np.float32)  # AllocKeys.OutBuffer, :1610
+    for k in range(kv):                                            # convops.py:1612-1631
         if subm and k == kv // 2:
             continue
         n = int(cnt[k])
         if n <= 0:
             continue
-        buf = x[pin[k, :n]] @ w[:, k].T
-        np.add.at(out, pout[k, :n], buf)
+        gather_rows(inp_buffer, x, np.ascontiguousarray(pin[k, :n]))
+        _mm(inp_buffer[:n], w[:, k].T, out=out_buffer[:n])
+        scatter_add_rows(out, out_buffer, np.ascontiguousarray(pout[k, :n]))
     if bias is not None:
         out = out + np.asarray(bias, dtype=np.float32)
     return apply_act(out, act, act_alpha)
@@ -234,29 +326,33 @@ def indice_conv_backward(features: np.ndarray, filters: np.ndarray, out_bp: np.n
                          subm: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """fp32 backward (``convops.py:1769-1860``): ``dW_k = dout[po]^T @ x[pi]``,
     ``din[pi] += dout[po] @ W_k``.  Returns ``(din [N,C], dfilters KRSC)``."""
-    x = np.asarray(features, dtype=np.float32)
-    dout = np.asarray(out_bp, dtype=np.float32)
+    x = np.ascontiguousarray(features, dtype=np.float32)
+    dout = np.ascontiguousarray(out_bp, dtype=np.float32)
     K, C = filters.shape[0], filters.shape[-1]
-    w = np.asarray(filters, dtype=np.float32).reshape(K, -1, C)
+    w = np.ascontiguousarray(filters, dtype=np.float32).reshape(K, -1, C)
     kv = w.shape[1]
     cnt = _pair_counts(num, kv, x.shape[0], subm)
     dw = np.zeros_like(w)
     if subm:
-        dw[:, kv // 2] = dout.T @ x                   # cppcore.py:314-317
-        din = dout @ w[:, kv // 2]
+        dw[:, kv // 2] = _mm(dout.T, x)               # cppcore.py:314-317
+        din = np.ascontiguousarray(_mm(dout, w[:, kv // 2]))
     else:
         din = np.zeros_like(x)
     pin, pout = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])
-    for k in range(kv):
+    maxnhot = int(max([cnt[k] for k in range(kv) if not (subm and k == kv // 2)] + [0]))
+    inp_buffer = np.empty((max(maxnhot, 1), C), dtype=np.float32)
+    out_buffer = np.empty((max(maxnhot, 1), K), dtype=np.float32)
+    for k in range(kv):                               # convops.py:1831-1860
         if subm and k == kv // 2:
             continue
         n = int(cnt[k])
         if n <= 0:
             continue
-        og = dout[pout[k, :n]]
-        ig = x[pin[k, :n]]
-        dw[:, k] = og.T @ ig
-        np.add.at(din, pin[k, :n], og @ w[:, k])
+        gather_rows(inp_buffer, x, np.ascontiguousarray(pin[k, :n]))
+        gather_rows(out_buffer, dout, np.ascontiguousarray(pout[k, :n]))
+        dw[:, k] = _mm(out_buffer[:n].T, inp_buffer[:n])          # KN @ NC  (cppcore.py:341-343)
+        _mm(out_buffer[:n], w[:, k], out=inp_buffer[:n])          # NK @ KC  (cppcore.py:347-348)
+        scatter_add_rows(din, inp_buffer, np.ascontiguousarray(pin[k, :n]))
     return din, dw.reshape(filters.shape)
 
 

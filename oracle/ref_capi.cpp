@@ -1,0 +1,75 @@
+// C entry points over the reference's own CPU code (oracle/_ref/spconv_ref_gen.h, extracted from
+// /root/reference by oracle/make_ref.py).  Same signatures as the restatement in spconv_oracle.c so
+// tests can run both on identical inputs.  TEST INFRASTRUCTURE ONLY.
+#include "_ref/spconv_ref_gen.h"
+
+namespace {
+template <int ND> tv::array<int, ND> arr(const int *p) {
+    tv::array<int, ND> a;
+    for (int i = 0; i < ND; ++i) a[i] = p[i];
+    return a;
+}
+tv::Tensor t_i32(const void *p, std::vector<int64_t> shape) { return tv::Tensor(const_cast<void *>(p), std::move(shape), tv::int32); }
+tv::Tensor t_f32(const void *p, std::vector<int64_t> shape) { return tv::Tensor(const_cast<void *>(p), std::move(shape), tv::float32); }
+}  // namespace
+
+#define REF_DISPATCH_NDIM(ndim, EXPR)                                                     \
+    switch (ndim) {                                                                       \
+        case 1: { namespace R = ref_nd1; constexpr int ND = 1; EXPR; } break;             \
+        case 2: { namespace R = ref_nd2; constexpr int ND = 2; EXPR; } break;             \
+        case 3: { namespace R = ref_nd3; constexpr int ND = 3; EXPR; } break;             \
+        case 4: { namespace R = ref_nd4; constexpr int ND = 4; EXPR; } break;             \
+        default: return -1;                                                               \
+    }
+
+extern "C" {
+
+// pairs [2, kv, N] pre-filled with -1, num [kv] zeroed by the caller (spconv/csrc/sparse/all.py:2071-2075)
+int ref_subm_rulebook(const int32_t *indices, int N, int ndim, int batch_size, const int *dims, const int *ksize,
+                      const int *dilation, int32_t *pairs, int32_t *num) {
+    int kv = 1;
+    for (int a = 0; a < ndim; ++a) kv *= ksize[a];
+    try {
+        REF_DISPATCH_NDIM(ndim, return R::SparseConvIndicesCPU::generate_subm_conv_inds(
+            t_i32(indices, {N, ndim + 1}), t_i32(pairs, {2, kv, N}), tv::Tensor(), t_i32(num, {kv}), batch_size,
+            arr<ND>(dims), arr<ND>(ksize), arr<ND>(dilation)));
+    } catch (const std::exception &e) {
+        return std::strstr(e.what(), "odd ksize") ? -2 : -3;
+    }
+    return -1;
+}
+
+// out_inds must hold kv * N rows (all.py:2121); returns the number of active outputs
+int ref_conv_rulebook(const int32_t *indices, int N, int ndim, int batch_size, const int *out_dims,
+                      const int *in_dims, const int *ksize, const int *stride, const int *padding,
+                      const int *dilation, int transposed, int32_t *pairs, int32_t *out_inds, int32_t *num) {
+    int kv = 1;
+    for (int a = 0; a < ndim; ++a) kv *= ksize[a];
+    try {
+        REF_DISPATCH_NDIM(ndim, return R::SparseConvIndicesCPU::generate_conv_inds(
+            t_i32(indices, {N, ndim + 1}), t_i32(pairs, {2, kv, N}), t_i32(out_inds, {(int64_t)kv * N, ndim + 1}),
+            t_i32(num, {kv}), batch_size, arr<ND>(out_dims), arr<ND>(in_dims), arr<ND>(ksize), arr<ND>(stride),
+            arr<ND>(padding), arr<ND>(dilation), transposed != 0));
+    } catch (const std::exception &) {
+        return -3;
+    }
+    return -1;
+}
+
+void ref_gather_f32(float *buf, const float *src, const int32_t *inds, int n, int channels, int src_rows) {
+    GatherCPU::gather(t_f32(buf, {n, channels}), t_f32(src, {src_rows, channels}), t_i32(inds, {n}));
+}
+
+void ref_scatter_add_f32(float *dst, const float *buf, const int32_t *inds, int n, int channels, int dst_rows) {
+    GatherCPU::scatter_add(t_f32(dst, {dst_rows, channels}), t_f32(buf, {n, channels}), t_i32(inds, {n}));
+}
+
+int ref_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

@@ -6,14 +6,16 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / the timed host baseline.
  *
- * Parity status: the reference (traveller59/spconv v2.3.8) cannot be built in this
- * image (pccm / cumm / ccimport absent, no network), and its own tests hold no
- * stored rulebook vectors ("parity unpinned" for the pair ORDER).  What pins this file:
- *   (1) it follows the reference algorithm text line by line (citations below);
- *   (2) tests/test_oracle.py checks its rulebooks through the reference's own
- *       dense-convolution equivalence test (test/test_conv.py:247-357) and against
- *       the facts BASELINE.md records for the reference fixture (P = 788 888,
- *       M = 136 998 for test/data/test_spconv.pkl).
+ * Parity status: PINNED TO THE REFERENCE ITSELF.  The reference's package cannot be built in
+ * this image (pccm / cumm / ccimport absent, no network), but its CPU rulebook is plain C++ held
+ * in Python f-strings; oracle/make_ref.py extracts that text from /root/reference, compiles it
+ * with g++ into oracle/_ref/libspconv_ref.so, and tests/test_oracle_ref.py checks this file
+ * against it BIT FOR BIT (pair order, first-touch output order, counts, error cases) on config 1,
+ * on every rulebook geometry of the GPU parity tests (1-D .. 4-D, strided, dilated, transposed),
+ * on the reference's LiDAR fixture coordinates and on KITTI-shaped synthetic clouds.  In
+ * addition tests/test_oracle.py runs the reference's own dense-convolution equivalence
+ * criterion (test/test_conv.py:247-357) and the fixture facts of BASELINE.md section 2
+ * (P = 788 888, M = 136 998 for test/data/test_spconv.pkl).
  *
  * Reference locations restated here (all relative to /root/reference):
  *   spconv/csrc/sparse/indices.py:105-136   linear key = row-major over [batch, dims...];

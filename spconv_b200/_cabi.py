@@ -81,6 +81,7 @@ SIGNATURES = {
                                            c_float, c_void_p]),
     "spx_last_kernel_family": (c_int, []),
     "spx_launch_count": (c_int64, [c_int]),
+    "spx_debug_configure": (c_int, [c_int, c_int, c_int, c_void_p, c_size_t]),
 }
 
 _lib = None

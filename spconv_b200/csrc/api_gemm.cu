@@ -9,15 +9,9 @@ namespace spx {
 int write_tile_masks(const uint32_t *mask, int64_t rows, int kv, uint32_t *out, cudaStream_t stream);
 }
 
-// SPX_FORCE_SIMT=1 pins the generic kernels (debug / A-B comparisons in tests)
-static bool force_simt() {
-    const char *e = getenv("SPX_FORCE_SIMT");
-    return e && e[0] == '1';
-}
-static bool force_tc() {
-    const char *e = getenv("SPX_FORCE_TC");
-    return e && e[0] == '1';
-}
+// SPX_FORCE_SIMT=1 pins the generic kernels (debug / A-B comparisons in tests); read once at load
+static bool force_simt() { return runtime_cfg().force_simt != 0; }
+static bool force_tc() { return runtime_cfg().force_tc != 0; }
 
 static int check_desc(const spx_gemm_desc *d, const char *who) {
     SPX_REQUIRE(d != nullptr, "%s: descriptor is NULL", who);

@@ -18,6 +18,20 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 void set_family(int f);
 int sm_count();          // SMs of the current device (cached)
+int current_device();    // cudaGetDevice (0 on failure)
+
+// Process-wide switches.  SPX_FORCE_SIMT / SPX_FORCE_TC / SPX_TC_CTAS are read from the
+// environment ONCE, when the library is loaded; the perf-triage hooks (ablation bits, timeline
+// buffer) are only reachable through spx_debug_configure(), which validates the buffer.
+struct RuntimeCfg {
+    int force_simt = 0, force_tc = 0, tc_ctas = 2;
+    int debug = 0;                 // ablation bits, see gemm_tc.cu / gemm_tc_wgrad.cu
+    long long *trace = nullptr;    // [8][2048] int64 device buffer or NULL
+};
+RuntimeCfg &runtime_cfg();
+
+// cudaFuncSetAttribute is per DEVICE: remember which (function, device) pairs were configured
+bool func_configured(const void *fn, int dev);   // returns the previous state and marks it
 
 #define SPX_CHECK_CUDA(expr)                                                              \
     do {                                                                                  \

@@ -1,5 +1,7 @@
 // Library core: thread-local error string, launch counter, device check, elementwise epilogue.
 #include "common.cuh"
+#include <mutex>
+#include <stdlib.h>
 
 namespace spx {
 
@@ -15,6 +17,41 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 void set_family(int f) { g_family = f; }
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return dev;
+}
+
+static RuntimeCfg make_cfg_from_env() {
+    RuntimeCfg c;
+    const char *e = getenv("SPX_FORCE_SIMT");
+    c.force_simt = e && e[0] == '1';
+    e = getenv("SPX_FORCE_TC");
+    c.force_tc = e && e[0] == '1';
+    e = getenv("SPX_TC_CTAS");
+    c.tc_ctas = e ? atoi(e) : 2;
+    return c;
+}
+RuntimeCfg &runtime_cfg() {
+    static RuntimeCfg cfg = make_cfg_from_env();
+    return cfg;
+}
+
+bool func_configured(const void *fn, int dev) {
+    // tiny open table: at most a few dozen kernel instances need the opt-in
+    struct Entry { const void *fn; unsigned long long devs; };
+    static Entry tab[128];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned long long bit = 1ull << (dev & 63);
+    for (auto &e : tab) {
+        if (e.fn == fn) { const bool seen = e.devs & bit; e.devs |= bit; return seen; }
+        if (e.fn == nullptr) { e.fn = fn; e.devs = bit; return false; }
+    }
+    return false;   // table full: configure again (idempotent)
+}
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -53,6 +90,25 @@ extern "C" int64_t spx_launch_count(int reset) {
     int64_t v = g_launches;
     if (reset) g_launches = 0;
     return v;
+}
+
+extern "C" int spx_debug_configure(int force_family, int tc_ctas, int debug_bits, void *trace_buf, size_t trace_bytes) {
+    RuntimeCfg &c = runtime_cfg();
+    SPX_REQUIRE(force_family >= -1 && force_family <= 2, "debug_configure: force_family must be -1 (keep), 0 (auto), 1 (SIMT) or 2 (tcgen05)");
+    SPX_REQUIRE(trace_buf == nullptr || trace_bytes >= (size_t)8 * 2048 * sizeof(long long),
+                "debug_configure: trace buffer must hold [8][2048] int64 (%zu bytes), got %zu",
+                (size_t)8 * 2048 * sizeof(long long), trace_bytes);
+    if (trace_buf) {
+        cudaPointerAttributes attr;
+        SPX_CHECK_CUDA(cudaPointerGetAttributes(&attr, trace_buf));
+        SPX_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged,
+                    "debug_configure: trace buffer is not device memory");
+    }
+    if (force_family >= 0) { c.force_simt = force_family == 1; c.force_tc = force_family == 2; }
+    if (tc_ctas > 0) c.tc_ctas = tc_ctas;
+    c.debug = debug_bits;
+    c.trace = (long long *)trace_buf;
+    return 0;
 }
 
 extern "C" int spx_device_check(int dev, int *sm_count_out, int *cc_major, int *cc_minor) {

@@ -619,8 +619,8 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     while (cols < (uint32_t)(2 * cy)) cols <<= 1;
     p.tmem_cols = cols;
     // two CTAs per SM when >= 3 pipeline stages and both TMEM allocations fit; else one big CTA
-    const char *ctas_env = getenv("SPX_TC_CTAS");
-    const int want_ctas = ctas_env ? atoi(ctas_env) : 2;
+    const RuntimeCfg &cfg = runtime_cfg();
+    const int want_ctas = cfg.tc_ctas;
     p.ctas_per_sm = (want_ctas >= 2 && (TC_SMEM_BUDGET_2 - 2 * p.idx_bytes) / p.stage_bytes >= 3 && cols <= 256) ? 2 : 1;
     const int budget = p.ctas_per_sm == 2 ? TC_SMEM_BUDGET_2 : TC_SMEM_BUDGET;
     p.stages = (budget - 2 * p.idx_bytes) / p.stage_bytes;
@@ -635,22 +635,19 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     }
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
-    const char *dbg = getenv("SPX_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-    const char *trace = getenv("SPX_TC_TRACE");   // hex device pointer of a [4][2048] int64 buffer
-    p.dbg_ts = trace ? (long long *)strtoull(trace, nullptr, 16) : nullptr;
+    p.debug = cfg.debug;          // perf-triage hooks, set through spx_debug_configure() only
+    p.dbg_ts = cfg.trace;
     return 0;
 }
 
 template <int KIND, int CPR>
 static int launch_tc_cpr(const CUtensorMap &tm, const TcParams &p, cudaStream_t stream) {
     const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.idx_bytes + 1024 /*align slack*/ + 1024 /*barriers, tile-info ring*/;
-    static thread_local bool configured = false;
-    if (!configured) {
+    // the opt-in is a per-DEVICE attribute: one process may drive several GPUs
+    if (!func_configured((const void *)tc_gather_gemm_kernel<KIND, CPR>, current_device())) {
         SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(TC_SMEM_BUDGET + 2048)));
         SPX_CHECK_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<KIND, CPR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
     }
     const int64_t tiles = div_up64(p.rows, TC_TILE_M);
     const int64_t max_ctas = (int64_t)sm_count() * p.ctas_per_sm;

@@ -555,12 +555,8 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     WgPlan pl;
     SPX_REQUIRE(make_plan(a, pl), "tc_wgrad: unsupported shape");
     pl.p.partial = (float *)a.workspace;
-    {
-        const char *trace = getenv("SPX_TC_TRACE");
-        pl.p.dbg_ts = trace ? (long long *)strtoull(trace, nullptr, 16) : nullptr;
-        const char *dbg = getenv("SPX_TC_DEBUG");
-        pl.p.debug = dbg ? atoi(dbg) : 0;
-    }
+    pl.p.dbg_ts = runtime_cfg().trace;      // perf-triage hooks (spx_debug_configure)
+    pl.p.debug = runtime_cfg().debug;
     SPX_REQUIRE((size_t)pl.chunks * pl.p.partial_stride * sizeof(float) <= a.workspace_bytes,
                 "tc_wgrad: workspace too small");
     SPX_REQUIRE(((uintptr_t)a.workspace & 15u) == 0, "tc_wgrad: workspace must be 16-byte aligned");
@@ -574,15 +570,9 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
 #undef WG_PICK_ROW
 #undef WG_PICK
     SPX_REQUIRE(fn != nullptr, "tc_wgrad: no kernel instance for this channel layout");
-    static thread_local KernelFn configured[16] = {};
-    bool seen = false;
-    for (int i = 0; i < 16; ++i) seen |= configured[i] == fn;
-    if (!seen) {
+    if (!func_configured((const void *)fn, current_device()))      // per-device attribute
         SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             WG_SMEM_MAX));
-        for (int i = 0; i < 16; ++i)
-            if (!configured[i]) { configured[i] = fn; break; }
-    }
     fn<<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
     SPX_CHECK_LAUNCH("tc_wgrad_kernel");
     const int64_t total = pl.p.partial_stride;

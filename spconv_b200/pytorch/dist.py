@@ -36,19 +36,40 @@ class GradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        self._views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             assert p.dtype == dt, "one bucket per dtype"
-            # gradients accumulate straight into the bucket: no gather/scatter copies per step
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.attach()
+
+    def attach(self) -> int:
+        """(Re-)alias every ``p.grad`` to its slice of the bucket.  ``optimizer.zero_grad()`` and
+        ``module.zero_grad()`` default to ``set_to_none=True``, which drops the aliases; the next
+        backward then allocates fresh ``.grad`` tensors OUTSIDE the bucket.  A gradient found
+        outside is copied in before it is re-aliased, so nothing is lost.  Returns how many
+        parameters had to be re-attached."""
+        fixed = 0
+        for p, view in zip(self.params, self._views):
+            g = p.grad
+            if g is not None and g.data_ptr() == view.data_ptr() and g.shape == view.shape:
+                continue
+            if g is not None:
+                view.copy_(g)
+            p.grad = view
+            fixed += 1
+        return fixed
 
     def zero(self) -> None:
+        """Zero the gradients in place (use instead of ``zero_grad(set_to_none=True)``)."""
+        self.attach()
         self.flat.zero_()
 
     def all_reduce(self, group: Optional[dist.ProcessGroup] = None, average: bool = True,
                    async_op: bool = False):
         """Sum (or mean) the bucket over the data-parallel group: one NCCL launch per step."""
+        self.attach()          # gradients produced after a zero_grad(set_to_none=True) are pulled in
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         if average:

@@ -25,6 +25,18 @@ def _worker(rank, world, port, tmp):
     expect = sum(gathered) / world
     ok1 = torch.allclose(bucket.flat, expect, atol=1e-6)
     ok1 = ok1 and all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
+    # optimizer.zero_grad() defaults to set_to_none=True and drops the aliases: the bucket must
+    # pull the freshly allocated gradients back in instead of reducing stale zeros
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    opt.zero_grad()
+    assert all(p.grad is None for p in lin.parameters())
+    lin(x).sum().backward()
+    fresh = torch.cat([p.grad.reshape(-1) for p in lin.parameters()]).clone()
+    bucket.all_reduce(average=True)
+    gathered = [torch.zeros_like(fresh) for _ in range(world)]
+    dist.all_gather(gathered, fresh)
+    ok1 = ok1 and torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-6)
+    ok1 = ok1 and all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
     # stateless variant
     lin2 = torch.nn.Linear(4, 2)
     lin2(torch.full((3, 4), float(rank))).sum().backward()

@@ -6,6 +6,12 @@ from bench_utils import surface_cloud
 import spconv_b200.pytorch as spconv
 from spconv_b200.core import ConvAlgo
 from spconv_b200.pytorch import ops
+
+def _dbg(debug=0, trace=None, ctas=0):
+    """perf-triage hooks go through the explicit C-ABI call (spx_debug_configure), not the environment"""
+    from spconv_b200 import _cabi as _c
+    _c.check(_c.load().spx_debug_configure(-1, int(ctas), int(debug), None if trace is None else trace.data_ptr(),
+                                            0 if trace is None else trace.numel() * trace.element_size()), "debug_configure")
 dev = torch.device("cuda:0")
 shape=[41,1600,1408]; C=K=64
 rng=np.random.default_rng(50051)
@@ -23,13 +29,13 @@ def t(fn,n=20):
     return tot/n*1000
 res_all={}
 for ctas in ("1","2"):
-    os.environ["SPX_TC_CTAS"]=ctas
+    _dbg(0, None, int(ctas))
     out={}
     for dbg in [0,1,2,4,8,15]:
-        os.environ["SPX_TC_DEBUG"]=str(dbg)
+        _dbg(dbg, None, int(ctas))
         f=t(lambda: ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True))
         out[dbg]=round(f,1)
-    os.environ["SPX_TC_DEBUG"]="0"
+    _dbg(0, None, int(ctas))
     bw=t(lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True))
     res_all[ctas]={"fwd_us_by_debug":out,"bwd_us":round(bw,1)}
 # host overhead of one op call (empty problem is not possible; time a tiny 128-row problem)

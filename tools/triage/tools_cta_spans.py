@@ -6,6 +6,12 @@ import numpy as np, torch
 from bench_utils import surface_cloud
 from spconv_b200.core import ConvAlgo
 from spconv_b200.pytorch import ops
+
+def _dbg(debug=0, trace=None, ctas=0):
+    """perf-triage hooks go through the explicit C-ABI call (spx_debug_configure), not the environment"""
+    from spconv_b200 import _cabi as _c
+    _c.check(_c.load().spx_debug_configure(-1, int(ctas), int(debug), None if trace is None else trace.data_ptr(),
+                                            0 if trace is None else trace.numel() * trace.element_size()), "debug_configure")
 dev = torch.device("cuda:0")
 shape=[41,1600,1408]; C=K=64
 rng=np.random.default_rng(50051)
@@ -16,13 +22,12 @@ _,_,pf,pb,mf,mb,sf,sb,masks=res
 fwd=lambda: ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True)
 for _ in range(3): fwd()
 for dbg in ("0","15","1","2","4"):
-    os.environ["SPX_TC_DEBUG"]=dbg
     ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
-    os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
+    _dbg(int(dbg), ts)
     torch.cuda._sleep(400000)
     a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
     a.record(); fwd(); b.record(); torch.cuda.synchronize()
-    del os.environ["SPX_TC_TRACE"]
+    _dbg(0, None)
     t=ts.cpu().numpy()[6:8].reshape(-1)[:1024*4].reshape(-1,4)
     t=t[t[:,0]>0]
     t0=t[:,0].min()

@@ -5,6 +5,12 @@ import numpy as np, torch
 from bench_utils import surface_cloud
 from spconv_b200.core import ConvAlgo
 from spconv_b200.pytorch import ops
+
+def _dbg(debug=0, trace=None, ctas=0):
+    """perf-triage hooks go through the explicit C-ABI call (spx_debug_configure), not the environment"""
+    from spconv_b200 import _cabi as _c
+    _c.check(_c.load().spx_debug_configure(-1, int(ctas), int(debug), None if trace is None else trace.data_ptr(),
+                                            0 if trace is None else trace.numel() * trace.element_size()), "debug_configure")
 dev = torch.device("cuda:0")
 shape=[41,1600,1408]; C=K=64
 rng=np.random.default_rng(50051)
@@ -14,7 +20,7 @@ res=ops.get_indice_pairs_implicit_gemm(inds,1,shape,ConvAlgo.MaskImplicitGemm,[3
 _,_,pf,pb,mf,mb,sf,sb,masks=res
 for _ in range(3): ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True)
 ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
-os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
+_dbg(0, ts)
 ops.implicit_gemm(x,w,pf,mf,sf,100000,masks,True,True)
 torch.cuda.synchronize()
 t=ts.cpu().numpy()

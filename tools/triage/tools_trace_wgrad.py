@@ -5,6 +5,12 @@ import numpy as np, torch
 from bench_utils import surface_cloud
 from spconv_b200.core import ConvAlgo
 from spconv_b200.pytorch import ops
+
+def _dbg(debug=0, trace=None, ctas=0):
+    """perf-triage hooks go through the explicit C-ABI call (spx_debug_configure), not the environment"""
+    from spconv_b200 import _cabi as _c
+    _c.check(_c.load().spx_debug_configure(-1, int(ctas), int(debug), None if trace is None else trace.data_ptr(),
+                                            0 if trace is None else trace.numel() * trace.element_size()), "debug_configure")
 dev = torch.device("cuda:0")
 shape=[41,1600,1408]; C=K=64
 rng=np.random.default_rng(50051)
@@ -15,8 +21,7 @@ _,_,pf,pb,mf,mb,sf,sb,masks=res
 bw=lambda: ops.implicit_gemm_backward(x,w,dout,pf,pb,mf,mb,sf,sb,None,masks,128,True)
 for _ in range(3): bw()
 ts=torch.zeros((8,2048),dtype=torch.int64,device=dev)
-os.environ["SPX_TC_DEBUG"]=os.environ.get("WG_DEBUG","0")
-os.environ["SPX_TC_TRACE"]=hex(ts.data_ptr())
+_dbg(int(os.environ.get("WG_DEBUG","0")), ts)
 bw(); torch.cuda.synchronize()
 t=ts.cpu().numpy(); t0=t[3,0]
 rel=lambda a:[int(v-t0) for v in a if v>0]
