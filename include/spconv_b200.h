@@ -22,6 +22,11 @@
  *                                                    spconv/csrc/sparse/convops.py:1504-2071
  *   spx_bias_act_inplace
  *        <- InferenceOps.bias_add_act_inplace        spconv/csrc/sparse/inference.py:166-252
+ *   spx_indice_pool_fwd / spx_indice_pool_bwd / spx_global_pool_rearrange
+ *        <- SpconvOps.maxpool_forward / maxpool_backward / maxpool_implicit_gemm_forward /
+ *           maxpool_implicit_gemm_backward / avgpool_implicit_gemm_forward / _backward /
+ *           global_pool_rearrange                    spconv/csrc/sparse/all.py:664-905
+ *           (kernels spconv/csrc/sparse/maxpool.py:41-341)
  *
  * Conventions
  *   - all pointers are DEVICE pointers unless the name ends in `_host`;
@@ -226,6 +231,39 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
 /* x[r, j] = act(x[r, j] + bias[j])   in place; bias may be NULL */
 int spx_bias_act_inplace(void *x, const void *bias, int64_t rows, int cols, int dtype, int act,
                          float act_alpha, spx_stream_t stream);
+
+/* ------------------------------------------------------------------ pooling on the rulebook */
+
+/*
+ * out[o, :] = reduce over the offsets k with pair_fwd[k][o] >= 0 of x[pair_fwd[k][o], :]
+ *   mode 0  max, rows without any input get the dtype's lowest value
+ *           (SparseMaxPool, ConvAlgo.MaskImplicitGemm: maxpool.py:76-117)
+ *   mode 1  max with a floor of 0 (ConvAlgo.Native: the reference raises a zero-initialised buffer,
+ *           spconv/pytorch/ops.py:1910-1936 + maxpool.py:41-73); the caller passes the dense table
+ *           made by spx_pairs_to_table from the compact pairs
+ *   mode 2  mean over the valid inputs; count_out [n_out] int32 (may be NULL) receives their number
+ *           (SparseAvgPool: maxpool.py:211-259)
+ * channels * element size must be a multiple of 16 bytes.  dtype: f32 / f16 / bf16, int8 for max.
+ */
+int spx_indice_pool_fwd(int mode, const void *features, void *out, const int32_t *pair_fwd,
+                        int64_t pair_stride, int kv, int64_t n_out, int channels, int dtype,
+                        int32_t *count_out, spx_stream_t stream);
+/*
+ * Input gradient through pair_bwd [kv, n_in] (in -> out):
+ *   modes 0, 1  din[i] = sum_k (x[i] == y[o_k]) ? dy[o_k] : 0        (maxpool.py:120-208)
+ *   mode 2      din[i] = sum_k dy[o_k] * count_out[o_k]              (maxpool.py:262-300, as is)
+ */
+int spx_indice_pool_bwd(int mode, const void *features, const void *out_features, const void *out_bp,
+                        void *din, const int32_t *pair_bwd, int64_t pair_stride, int kv, int64_t n_in,
+                        int channels, int dtype, const int32_t *count_out, spx_stream_t stream);
+/*
+ * Rows of every sample in input order: out_indices [batch_size, n] (only the first counts[b]
+ * entries of row b are written), counts [batch_size]; coords [n, row_ints] with the batch index
+ * first.  Deterministic (the reference appends with atomics, maxpool.py:303-341; the CPU version
+ * keeps input order, :599-620).
+ */
+int spx_global_pool_rearrange(const int32_t *coords, int64_t n, int row_ints, int batch_size,
+                              int32_t *out_indices, int32_t *counts, spx_stream_t stream);
 
 /*
  * int8 inference forward (reference formula: test/test_all_algo.py:272-287,

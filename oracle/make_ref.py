@@ -8,6 +8,8 @@ The reference's CPU implementation of this path is plain C++ held in Python f-st
 * ``spconv/csrc/sparse/indices.py:1621-1778`` ``SparseConvIndicesCPU`` (``generate_subm_conv_inds``,
   ``generate_conv_inds``: the hash-map rulebook loops)
 * ``spconv/csrc/sparse/gather.py:30-86``      ``GatherCPU`` (``gather`` / ``scatter_add``)
+* ``spconv/csrc/sparse/maxpool.py:590-700``   ``IndiceMaxPoolCPU`` (``forward`` / ``backward`` /
+  ``global_pool_rearrange``)
 
 ``pccm`` / ``cumm`` / ``ccimport`` are not installable here (no network), so the reference's own
 build cannot run.  This script instead *executes the reference's generator methods* against a
@@ -42,7 +44,7 @@ GEN_HDR = os.path.join(OUT_DIR, "spconv_ref_gen.h")
 LIB = os.path.join(OUT_DIR, "libspconv_ref.so")
 SHIM = os.path.join(HERE, "ref_shim.h")
 CAPI = os.path.join(HERE, "ref_capi.cpp")
-REF_FILES = ["spconv/csrc/sparse/indices.py", "spconv/csrc/sparse/gather.py"]
+REF_FILES = ["spconv/csrc/sparse/indices.py", "spconv/csrc/sparse/gather.py", "spconv/csrc/sparse/maxpool.py"]
 
 
 def reference_available() -> bool:
@@ -167,6 +169,9 @@ def _install_stubs():
     mod("spconv.csrc")
     mod("spconv.csrc.sparse")
     mod("spconv.csrc.sparse.cpu_core")
+    mod("spconv.csrc.utils")
+    mod("spconv.csrc.utils.launch")
+    mod("cumm.gemm.mask_iters")
     return dtypes
 
 
@@ -194,6 +199,7 @@ def generate() -> str:
     dtypes = _install_stubs()
     ind = _load(os.path.join(REF_ROOT, REF_FILES[0]), "_ref_indices")
     gat = _load(os.path.join(REF_ROOT, REF_FILES[1]), "_ref_gather")
+    mpl = _load(os.path.join(REF_ROOT, REF_FILES[2]), "spconv.csrc.sparse.maxpool")   # has a relative import
     out = ["// GENERATED by oracle/make_ref.py from the reference's own C++ text -- do not commit.\n",
            '#pragma once\n#include "../ref_shim.h"\n']
     for ndim in (1, 2, 3, 4):
@@ -228,6 +234,12 @@ def generate() -> str:
     out.append(_emit_fn("gather", g.gather(), True))
     out.append(_emit_fn("scatter_add", g.scatter_add(), True))
     out.append("};\n")
+    mp = mpl.IndiceMaxPoolCPU()
+    out.append("struct IndiceMaxPoolCPU {\n")
+    out.append(_emit_fn("global_pool_rearrange", mp.global_pool_rearrange(), True))
+    out.append(_emit_fn("forward", mp.forward(), True))
+    out.append(_emit_fn("backward", mp.backward(), True))
+    out.append("};\n")
     return "".join(out)
 
 
@@ -250,7 +262,10 @@ def build(force: bool = False, verbose: bool = False) -> Optional[str]:
                 del sys.modules[k]
     with open(GEN_HDR, "w") as f:
         f.write(text)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-Wno-unused-variable",
+    # No -fopenmp: the reference's default (CUDA) build compiles GatherCPU without OMPLib
+    # (gather.py:25-26: OpenMP only when CUMM_CPU_ONLY_BUILD), and a second OpenMP runtime next to
+    # torch's own thread pool makes every parallel region ~100x slower (measured: 0.17 -> 47 ms).
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-variable",
            "-I", HERE, "-o", LIB, CAPI]
     if verbose:
         print(" ".join(cmd))

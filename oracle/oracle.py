@@ -248,15 +248,16 @@ def implicit_gemm_tables(pairs: np.ndarray, num: np.ndarray, n_in: int, n_out: i
 
 
 def _mm(a: np.ndarray, b: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
-    """The reference's mm callback is ``torch.mm`` on the host BLAS (``cppcore.py:232-348``)."""
+    """The reference's mm callback is ``torch.mm`` on the host BLAS (``cppcore.py:232-348``);
+    transposed operands are passed as strided views (no copies), as ``tensor.T`` is there."""
     try:
         import torch
     except Exception:                                   # pragma: no cover
         return np.matmul(a, b, out=out)
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)    # from_numpy keeps numpy's strides
     if out is None:
-        return torch.mm(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b))).numpy()
-    torch.mm(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b)),
-             out=torch.from_numpy(out))
+        return torch.mm(ta, tb).numpy()
+    torch.mm(ta, tb, out=torch.from_numpy(out))
     return out
 
 
@@ -421,3 +422,110 @@ def generate_sparse_data(shape, num_points, num_channels, rng: np.random.Generat
                         size=(indices.shape[0], num_channels)).astype(dtype)
     assert indices.shape[1] == ndim + 1
     return feats, indices
+
+
+# ---------------------------------------------------------------------------- pooling
+def indice_maxpool(features: np.ndarray, pairs: np.ndarray, num: np.ndarray, num_activate_out: int) -> np.ndarray:
+    """ConvAlgo.Native max pooling: a ZERO-initialised output raised offset by offset
+    (``spconv/pytorch/ops.py:1899-1936`` + ``IndiceMaxPoolCPU::forward``, ``maxpool.py:623-658``);
+    runs the reference's own loop when ``oracle/_ref`` is built."""
+    x = np.ascontiguousarray(features, dtype=np.float32)
+    out = np.zeros((int(num_activate_out), x.shape[1]), dtype=np.float32)
+    r = ref_lib()
+    for k in range(pairs.shape[1]):
+        n = int(num[k])
+        if n <= 0:
+            continue
+        pi, po = np.ascontiguousarray(pairs[0, k, :n]), np.ascontiguousarray(pairs[1, k, :n])
+        if r is not None:
+            r.ref_maxpool_fwd_f32(_ptr(out), _ptr(x), _ptr(po), _ptr(pi), n, x.shape[1], out.shape[0], x.shape[0])
+        else:
+            np.maximum.at(out, po, x[pi])
+    return out
+
+
+def indice_maxpool_backward(features, out_features, out_bp, pairs, num) -> np.ndarray:
+    """``din[i] += dout[o]`` where ``x[i] == y[o]`` (``ops.py:1939-1972``, ``maxpool.py:661-700``)."""
+    x = np.ascontiguousarray(features, dtype=np.float32)
+    y = np.ascontiguousarray(out_features, dtype=np.float32)
+    dy = np.ascontiguousarray(out_bp, dtype=np.float32)
+    din = np.zeros_like(x)
+    r = ref_lib()
+    for k in range(pairs.shape[1]):
+        n = int(num[k])
+        if n <= 0:
+            continue
+        pi, po = np.ascontiguousarray(pairs[0, k, :n]), np.ascontiguousarray(pairs[1, k, :n])
+        if r is not None:
+            r.ref_maxpool_bwd_f32(_ptr(y), _ptr(x), _ptr(dy), _ptr(din), _ptr(po), _ptr(pi), n, x.shape[1],
+                                  y.shape[0], x.shape[0])
+        else:
+            np.add.at(din, pi, np.where(x[pi] == y[po], dy[po], 0))
+    return din
+
+
+def maxpool_implicit_gemm(features: np.ndarray, pair_fwd: np.ndarray, lowest: float) -> np.ndarray:
+    """``forward_implicit_gemm_kernel`` (``maxpool.py:76-117``, CUDA only in the reference):
+    max over the valid entries of ``pair_fwd[:, o]``, starting from the dtype's lowest value."""
+    x = np.asarray(features, dtype=np.float32)
+    kv, m = pair_fwd.shape
+    out = np.full((m, x.shape[1]), lowest, dtype=np.float32)
+    for k in range(kv):
+        o = np.nonzero(pair_fwd[k] >= 0)[0]
+        out[o] = np.maximum(out[o], x[pair_fwd[k, o]])
+    return out
+
+
+def maxpool_implicit_gemm_backward(features, out_features, out_bp, pair_bwd) -> np.ndarray:
+    """``backward_implicit_gemm_kernel`` (``maxpool.py:159-208``)."""
+    x, y, dy = (np.asarray(a, dtype=np.float32) for a in (features, out_features, out_bp))
+    din = np.zeros_like(x)
+    for k in range(pair_bwd.shape[0]):
+        i = np.nonzero(pair_bwd[k] >= 0)[0]
+        o = pair_bwd[k, i]
+        din[i] += np.where(x[i] == y[o], dy[o], 0)
+    return din
+
+
+def avgpool_implicit_gemm(features: np.ndarray, pair_fwd: np.ndarray):
+    """``forward_avgpool_implicit_gemm_kernel`` (``maxpool.py:211-259``): mean over the valid
+    entries; returns ``(out, count)``."""
+    x = np.asarray(features, dtype=np.float32)
+    kv, m = pair_fwd.shape
+    acc = np.zeros((m, x.shape[1]), dtype=np.float32)
+    count = (pair_fwd >= 0).sum(axis=0).astype(np.int32)
+    for k in range(kv):
+        o = np.nonzero(pair_fwd[k] >= 0)[0]
+        acc[o] += x[pair_fwd[k, o]]
+    out = np.where(count[:, None] > 0, acc / np.maximum(count, 1)[:, None].astype(np.float32), 0).astype(np.float32)
+    return out, count
+
+
+def avgpool_implicit_gemm_backward(out_bp, pair_bwd, count) -> np.ndarray:
+    """``backward_avgpool_implicit_gemm_kernel`` (``maxpool.py:262-300``): the reference MULTIPLIES the
+    upstream gradient by the neighbour count; restated as is."""
+    dy = np.asarray(out_bp, dtype=np.float32)
+    din = np.zeros((pair_bwd.shape[1], dy.shape[1]), dtype=np.float32)
+    for k in range(pair_bwd.shape[0]):
+        i = np.nonzero(pair_bwd[k] >= 0)[0]
+        o = pair_bwd[k, i]
+        din[i] += dy[o] * count[o][:, None].astype(np.float32)
+    return din
+
+
+def global_pool_rearrange(coords: np.ndarray, batch_size: int):
+    """``IndiceMaxPoolCPU::global_pool_rearrange`` (``maxpool.py:599-620``)."""
+    coords = np.ascontiguousarray(coords, dtype=np.int32)
+    n = coords.shape[0]
+    out = np.zeros((batch_size, n), dtype=np.int32)
+    counts = np.zeros((batch_size,), dtype=np.int32)
+    r = ref_lib()
+    if r is not None:
+        r.ref_global_pool_rearrange(_ptr(out), _ptr(coords), _ptr(counts), n, coords.shape[1], batch_size)
+    else:
+        for i in range(n):
+            b = coords[i, 0]
+            if b >= 0:
+                out[b, counts[b]] = i
+                counts[b] += 1
+    return out, counts

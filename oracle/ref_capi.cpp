@@ -64,6 +64,28 @@ void ref_scatter_add_f32(float *dst, const float *buf, const int32_t *inds, int 
     GatherCPU::scatter_add(t_f32(dst, {dst_rows, channels}), t_f32(buf, {n, channels}), t_i32(inds, {n}));
 }
 
+// one offset of the Native max pool: out[out_inds[i]] = max(out[..], in[in_inds[i]])  (maxpool.py:623-658)
+void ref_maxpool_fwd_f32(float *out, const float *in, const int32_t *out_inds, const int32_t *in_inds, int nhot,
+                         int channels, int out_rows, int in_rows) {
+    IndiceMaxPoolCPU::forward(t_f32(out, {out_rows, channels}), t_f32(in, {in_rows, channels}), t_i32(out_inds, {nhot}),
+                              t_i32(in_inds, {nhot}));
+}
+
+// din[in_inds[i]] += dout[out_inds[i]] where in == out   (maxpool.py:661-700)
+void ref_maxpool_bwd_f32(const float *out, const float *in, const float *dout, float *din, const int32_t *out_inds,
+                         const int32_t *in_inds, int nhot, int channels, int out_rows, int in_rows) {
+    IndiceMaxPoolCPU::backward(t_f32(out, {out_rows, channels}), t_f32(in, {in_rows, channels}),
+                               t_f32(dout, {out_rows, channels}), t_f32(din, {in_rows, channels}),
+                               t_i32(out_inds, {nhot}), t_i32(in_inds, {nhot}));
+}
+
+// out_indices [batch, n], counts [batch] zeroed by the caller   (maxpool.py:599-620)
+void ref_global_pool_rearrange(int32_t *out_indices, const int32_t *coords, int32_t *counts, int n, int row_ints,
+                               int batch) {
+    IndiceMaxPoolCPU::global_pool_rearrange(t_i32(out_indices, {batch, n}), t_i32(coords, {n, row_ints}),
+                                            t_i32(counts, {batch}));
+}
+
 int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -14,7 +14,8 @@
  *                              same rule as spconv/pytorch/ops.py:188-190: int64 keys once
  *                              N * prod(output_dims) reaches INT32_MAX)
  *   tv::dispatch / kernel_1d   dtype dispatch (fp32 / fp64 only here) and the 1-D CPU loop helper
- *                              (OpenMP ranges, as cumm's CPU-only build does)
+ *                              (one serial range: the reference's default build has no OpenMP in
+ *                              GatherCPU, gather.py:25-26; -fopenmp would split it into ranges)
  */
 #pragma once
 #include <cstdint>
@@ -75,6 +76,11 @@ struct Tensor {
     Tensor() = default;
     Tensor(void *p, std::vector<int64_t> s, DType d) : ptr(p), shape(std::move(s)), dt(d) {}
     int64_t dim(int i) const { return shape[i]; }
+    int64_t stride(int i) const {                 // contiguous row-major views only
+        int64_t s = 1;
+        for (size_t j = i + 1; j < shape.size(); ++j) s *= shape[j];
+        return s;
+    }
     template <typename T> T *data_ptr() const { return reinterpret_cast<T *>(const_cast<void *>(ptr)); }
     DType dtype() const { return dt; }
     int device() const { return -1; }

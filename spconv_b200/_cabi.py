@@ -79,6 +79,11 @@ SIGNATURES = {
     "spx_implicit_gemm_fwd_int8": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p,
                                            c_int, c_void_p, c_void_p, c_void_p, c_float, c_int,
                                            c_float, c_void_p]),
+    "spx_indice_pool_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int,
+                                    c_void_p, c_void_p]),
+    "spx_indice_pool_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "spx_global_pool_rearrange": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "spx_last_kernel_family": (c_int, []),
     "spx_launch_count": (c_int64, [c_int]),
     "spx_debug_configure": (c_int, [c_int, c_int, c_int, c_void_p, c_size_t]),

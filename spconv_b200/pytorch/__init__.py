@@ -10,3 +10,5 @@ from .core import (CUDAKernelTimer, ImplicitGemmIndiceData, IndiceData,  # noqa:
                    SparseConvTensor, scatter_nd)
 from .modules import (RemoveGrid, SparseBatchNorm, SparseIdentity, SparseModule,  # noqa: F401
                       SparseReLU, SparseSequential, ToDense, assign_name_for_sparse_modules)
+from .pool import (SparseAvgPool1d, SparseAvgPool2d, SparseAvgPool3d, SparseGlobalAvgPool,  # noqa: F401
+                   SparseGlobalMaxPool, SparseMaxPool1d, SparseMaxPool2d, SparseMaxPool3d, SparseMaxPool4d)

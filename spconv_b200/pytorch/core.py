@@ -51,6 +51,21 @@ class CUDAKernelTimer:
             finish.record()
             self._events.setdefault(".".join([*self._scope, name]), []).append((begin, finish))
 
+    def snapshot(self) -> Tuple[str, ...]:
+        """The current namespace stack (autograd Functions keep it so that the backward regions of
+        a layer land under the same prefix as its forward regions)."""
+        return tuple(self._scope)
+
+    @contextmanager
+    def scoped(self, scope: Sequence[str]):
+        saved = self._scope
+        if self.enable:
+            self._scope = list(scope)
+        try:
+            yield self
+        finally:
+            self._scope = saved
+
     def get_all_pair_time(self) -> Dict[str, float]:
         if not self.enable:
             return {}

@@ -41,6 +41,7 @@ class _NativeConv(Function):
                 timer, bias, act_alpha, act_beta, act_type, inverse, subm):
         ctx.save_for_backward(indice_pairs, indice_pair_num, features, filters)
         ctx.spx = (algo, timer, inverse, subm)
+        ctx.spx_scope = timer.snapshot()
         try:
             return ops.indice_conv(features, filters, indice_pairs, indice_pair_num,
                                    num_activate_out, inverse, subm, algo=algo, timer=timer,
@@ -59,9 +60,10 @@ class _NativeConv(Function):
         indice_pairs, indice_pair_num, features, filters = ctx.saved_tensors
         algo, timer, inverse, subm = ctx.spx
         try:
-            din, dw = ops.indice_conv_backward(features, filters, grad_output, indice_pairs,
-                                               indice_pair_num, inverse, subm, algo=algo,
-                                               timer=timer)
+            with timer.scoped(ctx.spx_scope):
+                din, dw = ops.indice_conv_backward(features, filters, grad_output, indice_pairs,
+                                                   indice_pair_num, inverse, subm, algo=algo,
+                                                   timer=timer)
         except Exception:
             _report("indice_conv_backward", feat=tuple(features.shape), w=tuple(filters.shape),
                     pair=tuple(indice_pairs.shape), do=tuple(grad_output.shape))
@@ -95,6 +97,7 @@ class SparseImplicitGemmFunction(Function):
             raise
         ctx.save_for_backward(features, filters, pair_fwd, pair_bwd)
         ctx.spx = dict(mask_width=mask_width, mask_out=mask_out, timer=timer, masks=masks,
+                       scope=timer.snapshot(),
                        is_subm=is_subm, fp32_accum=fp32_accum,
                        mask_fwd=pair_mask_fwd_splits, mask_bwd=pair_mask_bwd_splits,
                        sort_fwd=mask_argsort_fwd_splits, sort_bwd=mask_argsort_bwd_splits)
@@ -107,16 +110,75 @@ class SparseImplicitGemmFunction(Function):
         features, filters, pair_fwd, pair_bwd = ctx.saved_tensors
         s = ctx.spx
         try:
-            din, dw = ops.implicit_gemm_backward(
-                features, filters, grad_output, pair_fwd, pair_bwd, s["mask_fwd"], s["mask_bwd"],
-                s["sort_fwd"], s["sort_bwd"], mask_output_fwd=s["mask_out"], masks=s["masks"],
-                mask_width=s["mask_width"], is_subm=s["is_subm"], timer=s["timer"],
-                fp32_accum=s["fp32_accum"])
+            with s["timer"].scoped(s["scope"]):
+                din, dw = ops.implicit_gemm_backward(
+                    features, filters, grad_output, pair_fwd, pair_bwd, s["mask_fwd"], s["mask_bwd"],
+                    s["sort_fwd"], s["sort_bwd"], mask_output_fwd=s["mask_out"], masks=s["masks"],
+                    mask_width=s["mask_width"], is_subm=s["is_subm"], timer=s["timer"],
+                    fp32_accum=s["fp32_accum"])
         except Exception:
             _report("implicit_gemm_backward", feat=tuple(features.shape), w=tuple(filters.shape),
                     pair=tuple(pair_fwd.shape), issubm=s["is_subm"], do=tuple(grad_output.shape))
             raise
         return (din, dw) + (None,) * 16
+
+
+class SparseMaxPoolFunction(Function):
+    """ConvAlgo.Native max pooling (reference ``functional.py:360-378``)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, features, indice_pairs, indice_pair_num, num_activate_out):
+        out = ops.indice_maxpool(features, indice_pairs, indice_pair_num, num_activate_out)
+        ctx.save_for_backward(indice_pairs, indice_pair_num, features, out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        indice_pairs, indice_pair_num, features, out = ctx.saved_tensors
+        return ops.indice_maxpool_backward(features, out, grad_output, indice_pairs,
+                                           indice_pair_num), None, None, None
+
+
+class SparseMaxPoolImplicitGemmFunction(Function):
+    """Reference ``functional.py:381-400``."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, features, indice_pairs_fwd, indice_pairs_bwd, num_activate_out):
+        out = ops.indice_maxpool_implicit_gemm(features, indice_pairs_fwd, num_activate_out)
+        ctx.save_for_backward(indice_pairs_bwd, features, out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        indice_pairs_bwd, features, out = ctx.saved_tensors
+        return ops.indice_maxpool_implicit_gemm_backward(features, out, grad_output,
+                                                         indice_pairs_bwd), None, None, None
+
+
+class SparseAvgPoolImplicitGemmFunction(Function):
+    """Reference ``functional.py:403-423``."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, features, indice_pairs_fwd, indice_pairs_bwd, num_activate_out, calc_count):
+        out, count = ops.indice_avgpool_implicit_gemm(features, indice_pairs_fwd, num_activate_out,
+                                                      calc_count)
+        ctx.save_for_backward(indice_pairs_bwd, count)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        indice_pairs_bwd, count = ctx.saved_tensors
+        return ops.indice_avgpool_implicit_gemm_backward(grad_output, indice_pairs_bwd,
+                                                         count), None, None, None, None
 
 
 def _native(features, filters, indice_pairs, indice_pair_num, num_activate_out, algo, timer, bias,
@@ -148,3 +210,6 @@ def indice_subm_conv(features, filters, indice_pairs, indice_pair_num, num_activ
 
 
 implicit_gemm = SparseImplicitGemmFunction.apply
+indice_maxpool = SparseMaxPoolFunction.apply
+indice_maxpool_implicit_gemm = SparseMaxPoolImplicitGemmFunction.apply
+indice_avgpool_implicit_gemm = SparseAvgPoolImplicitGemmFunction.apply

@@ -568,6 +568,103 @@ def indice_conv_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: 
     return din, dfilters
 
 
+# ---------------------------------------------------------------------------- pooling
+_POOL_MAX, _POOL_MAX_ZERO_FLOOR, _POOL_MEAN = 0, 1, 2
+
+
+def _pool_check(features: torch.Tensor):
+    _require_cuda(features, "features")
+    if features.dtype not in _DTYPE_CODE:
+        raise RuntimeError(f"unsupported dtype {features.dtype}")
+    c = features.shape[1]
+    if (c * features.element_size()) % 16:
+        raise RuntimeError(f"pooling needs channels * element size to be a multiple of 16 bytes, got {c} x "
+                           f"{features.element_size()}")
+
+
+def _pool_fwd(mode, features, table, n_out, count_out=None):
+    features = features.contiguous()
+    _pool_check(features)
+    out = torch.empty((int(n_out), features.shape[1]), dtype=features.dtype, device=features.device)
+    _cabi.check(_lib().spx_indice_pool_fwd(mode, _ptr(features), _ptr(out), _ptr(table), int(table.stride(0)),
+                                           int(table.shape[0]), int(n_out), int(features.shape[1]),
+                                           _DTYPE_CODE[features.dtype], _ptr(count_out), _stream()),
+                "indice_pool_fwd")
+    return out
+
+
+def _pool_bwd(mode, features, out_features, out_bp, table_bwd, n_in, count_out=None):
+    out_bp = out_bp.contiguous()
+    _pool_check(out_bp)
+    din = torch.empty((int(n_in), out_bp.shape[1]), dtype=out_bp.dtype, device=out_bp.device)
+    _cabi.check(_lib().spx_indice_pool_bwd(mode, _ptr(features), _ptr(out_features), _ptr(out_bp), _ptr(din),
+                                           _ptr(table_bwd), int(table_bwd.stride(0)), int(table_bwd.shape[0]),
+                                           int(n_in), int(out_bp.shape[1]), _DTYPE_CODE[out_bp.dtype],
+                                           _ptr(count_out), _stream()), "indice_pool_bwd")
+    return din
+
+
+def indice_maxpool(features: torch.Tensor, indice_pairs: torch.Tensor, indice_pair_num: torch.Tensor,
+                   num_activate_out):
+    """ConvAlgo.Native max pooling over compact pairs (``ops.py:1899-1936``).  The reference raises a
+    zero-initialised output per offset, i.e. the result is ``max(0, max over inputs)``; the compact
+    pairs are scattered into a dense table on the device (no ``indice_pair_num.cpu()`` sync) and
+    one kernel reduces every output row."""
+    kv = int(indice_pairs.shape[1])
+    t_fwd, _, _, _ = _native_tables(indice_pairs.contiguous(), indice_pair_num, features.shape[0],
+                                    int(num_activate_out), kv, False, False, True, False)
+    return _pool_fwd(_POOL_MAX_ZERO_FLOOR, features, t_fwd, num_activate_out)
+
+
+def indice_maxpool_backward(features, out_features, out_bp, indice_pairs, indice_pair_num):
+    """``din[i] += dout[o]`` where ``x[i] == y[o]`` (``ops.py:1939-1972``)."""
+    kv = int(indice_pairs.shape[1])
+    _, _, t_bwd, _ = _native_tables(indice_pairs.contiguous(), indice_pair_num, features.shape[0],
+                                    out_features.shape[0], kv, False, False, False, True)
+    return _pool_bwd(_POOL_MAX, features.contiguous(), out_features.contiguous(), out_bp, t_bwd,
+                     features.shape[0])
+
+
+def indice_maxpool_implicit_gemm(features: torch.Tensor, indice_pairs: torch.Tensor, num_activate_out):
+    """Max pooling through the dense forward table ``pair_fwd [kv, M]`` (``ops.py:1975-2006``)."""
+    return _pool_fwd(_POOL_MAX, features, indice_pairs, num_activate_out)
+
+
+def indice_maxpool_implicit_gemm_backward(features, out_features, out_bp, indice_pairs):
+    """``indice_pairs`` is the backward table ``pair_bwd [kv, N]`` (``ops.py:2009-2030``)."""
+    return _pool_bwd(_POOL_MAX, features.contiguous(), out_features.contiguous(), out_bp, indice_pairs,
+                     features.shape[0])
+
+
+def indice_avgpool_implicit_gemm(features: torch.Tensor, indice_pairs: torch.Tensor, num_activate_out,
+                                 calc_count: bool):
+    """Mean over the valid neighbours + their count (``ops.py:2033-2074``)."""
+    count_out = torch.Tensor()
+    if calc_count:
+        count_out = torch.empty((int(num_activate_out),), dtype=torch.int32, device=features.device)
+    out = _pool_fwd(_POOL_MEAN, features, indice_pairs, num_activate_out, count_out if calc_count else None)
+    return out, count_out
+
+
+def indice_avgpool_implicit_gemm_backward(out_bp, indice_pairs, count_out):
+    """``din[i] = sum_o dout[o] * count[o]`` -- the reference multiplies by the neighbour count
+    (``maxpool.py:262-300``); kept so gradients equal the reference's (``ops.py:2077-2096``)."""
+    return _pool_bwd(_POOL_MEAN, None, None, out_bp, indice_pairs, indice_pairs.shape[1], count_out)
+
+
+def global_pool_rearrange(coords: torch.Tensor, batch_size: int):
+    """Row indices of every sample: ``(out_indices [batch, N], counts [batch])`` (``ops.py:2108-2124``)."""
+    _require_cuda(coords, "coords")
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    out_indices = torch.empty((batch_size, n), dtype=torch.int32, device=coords.device)
+    counts = torch.empty((batch_size,), dtype=torch.int32, device=coords.device)
+    _cabi.check(_lib().spx_global_pool_rearrange(_ptr(coords), n, int(coords.shape[1]), int(batch_size),
+                                                 _ptr(out_indices) if n else out_indices.data_ptr(),
+                                                 counts.data_ptr(), _stream()), "global_pool_rearrange")
+    return out_indices, counts
+
+
 # ---------------------------------------------------------------------------- misc
 def bias_add_act_inplace(x: torch.Tensor, bias: Optional[torch.Tensor], act_type=Activation.None_,
                          act_alpha: float = 0.0, act_beta: float = 0.0) -> torch.Tensor:

@@ -128,3 +128,25 @@ def test_subm_even_ksize_error_matches(ref):
     for impl in ("port", "ref"):
         with pytest.raises(RuntimeError, match="odd ksize"):
             ref.get_indice_pairs(inds, 1, [8, 8, 8], [2] * 3, [1] * 3, [0] * 3, [1] * 3, [0] * 3, True, impl=impl)
+
+
+def test_pooling_oracle_against_reference_cpu_loop(ref):
+    """IndiceMaxPoolCPU::forward / backward / global_pool_rearrange (maxpool.py:590-700, compiled into
+    oracle/_ref) vs the numpy restatements the GPU pooling tests use"""
+    rng = np.random.default_rng(0)
+    feats, inds = random_cloud(rng, [18, 20, 22], [1200, 900], 16)
+    o, pairs, num = ref.get_indice_pairs(inds, 2, [18, 20, 22], [3] * 3, [2] * 3, [1] * 3, [1] * 3, [0] * 3, False)
+    got = ref.indice_maxpool(feats, pairs, num, o.shape[0])              # runs the reference's loop
+    want = np.zeros_like(got)
+    for k in range(27):
+        np.maximum.at(want, pairs[1, k, :num[k]], feats[pairs[0, k, :num[k]]])
+    assert np.array_equal(got, want)
+    tabs = ref.implicit_gemm_tables(pairs, num, inds.shape[0], o.shape[0], False)
+    dense = ref.maxpool_implicit_gemm(feats, tabs["pair_fwd"], -3e38)
+    assert np.array_equal(np.maximum(dense, 0), got)                     # Native = zero floor
+    g = rng.standard_normal(got.shape).astype(np.float32)
+    d_ref = ref.indice_maxpool_backward(feats, dense, g, pairs, num)     # reference loop
+    d_np = ref.maxpool_implicit_gemm_backward(feats, dense, g, tabs["pair_bwd"])
+    assert np.abs(d_ref - d_np).max() < 1e-6
+    oi, cnt = ref.global_pool_rearrange(inds, 2)
+    assert cnt.tolist() == [1200, 900] and np.array_equal(oi[1, :900], np.arange(1200, 2100))
