@@ -3,6 +3,9 @@ import os
 
 # spconv/constants.py:37-42 -- weights are always KRSC in this engine
 SAVED_WEIGHT_LAYOUT = os.getenv("SPCONV_SAVED_WEIGHT_LAYOUT", "")
+if SAVED_WEIGHT_LAYOUT != "":
+    assert SAVED_WEIGHT_LAYOUT in ["KRSC", "RSKC", "RSCK"], \
+        "please set SAVED_WEIGHT_LAYOUT to KRSC, RSKC or RSCK"
 ALL_WEIGHT_IS_KRSC = True
 # spconv/constants.py:117 -- fp32 tensors multiply in exact fp32 unless TF32 is allowed
 SPCONV_ALLOW_TF32 = os.getenv("SPCONV_ALLOW_TF32", "0") == "1"

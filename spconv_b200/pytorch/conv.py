@@ -18,6 +18,7 @@ from torch.nn import functional as F
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
+from .. import constants as _constants
 from ..core import Activation, ConvAlgo
 from . import functional as Fsp
 from . import ops
@@ -96,6 +97,39 @@ class SparseConvolution(SparseModule):
         if record_voxel_count and not subm and not inverse:
             self.register_buffer(_MAX_NUM_VOXELS_DURING_TRAINING, torch.zeros(1, dtype=torch.int32))
         self.reset_parameters()
+        self._register_load_state_dict_pre_hook(self._load_weight_different_layout)
+
+    # ------------------------------------------------------------------ checkpoints
+    def get_max_num_voxels(self) -> Optional[torch.Tensor]:
+        return getattr(self, _MAX_NUM_VOXELS_DURING_TRAINING, None)
+
+    def _load_weight_different_layout(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs):
+        """``load_state_dict`` pre-hook (``spconv/pytorch/conv.py:648-683``): checkpoints written by
+        spconv 1.x / 2.1 hold filters as RSKC ``[*ksize, K, C]`` or RSCK ``[*ksize, C, K]``; with
+        ``SPCONV_SAVED_WEIGHT_LAYOUT`` set to that layout they are permuted to this engine's (and
+        spconv >= 2.2's) KRSC ``[K, *ksize, C]`` while loading.  Also supplies the voxel-count buffer
+        when an older checkpoint lacks it.
+
+        (The reference applies its permutation twice when ``ALL_WEIGHT_IS_KRSC`` -- :661-673 -- which
+        only round-trips for degenerate shapes; the conversion here is applied once.)"""
+        name = prefix + _MAX_NUM_VOXELS_DURING_TRAINING
+        if self.record_voxel_count and not self.subm and not self.inverse and name not in state_dict:
+            state_dict[name] = torch.zeros(1, dtype=torch.int32)
+        layout = _constants.SAVED_WEIGHT_LAYOUT
+        if not layout or layout == "KRSC":
+            return
+        key = prefix + "weight"
+        if key not in state_dict:
+            return
+        nd = self.ndim
+        w = state_dict[key]
+        if layout == "RSKC":
+            state_dict[key] = w.permute(nd, *range(nd), nd + 1).contiguous()
+        elif layout == "RSCK":
+            state_dict[key] = w.permute(nd + 1, *range(nd), nd).contiguous()
+        else:
+            raise ValueError(f"SPCONV_SAVED_WEIGHT_LAYOUT must be KRSC, RSKC or RSCK, got {layout!r}")
 
     # ------------------------------------------------------------------ parameters
     def reset_parameters(self):

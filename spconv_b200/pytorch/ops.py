@@ -9,7 +9,9 @@ CUDA stream.  CUDA tensors only: there is deliberately no CPU path in the produc
 Differences a reference user can observe (all documented in DESIGN.md):
   * rulebooks are deterministic and bit-equal to the reference's CPU order;
   * ``mask_width`` is always 128 (the tcgen05 tile height);
-  * ``ConvAlgo.MaskSplitImplicitGemm`` is executed as ``MaskImplicitGemm`` (one mask split).
+  * ``ConvAlgo.MaskSplitImplicitGemm`` builds the reference's two mask splits (offsets
+    ``[0, kv - kv//2)`` and the rest, ``ops.py:494-503``), sorts each on its own and runs one kernel
+    pass per split, summing the partial outputs (the reference accumulates with beta = 1).
 """
 from __future__ import annotations
 
@@ -170,6 +172,18 @@ def _argsort_masks(mask: torch.Tensor, kv: int, do_sort: bool, alloc) -> torch.T
     return argsort
 
 
+def _split_and_sort(mask: torch.Tensor, masks: List[np.ndarray], kv: int, do_sort: bool, alloc):
+    """mask [1, n, 1] (unsorted) -> per split j: (mask & masks[j]) sorted in place + its argsort
+    (``ops.py:494-503,538-549``: every split is sorted on its own)."""
+    mask_s, sort_s = [], []
+    for m in masks:
+        const = torch.from_numpy(m.view(np.int32).copy()).to(mask.device)
+        part = torch.bitwise_and(mask, const.view(1, 1, 1)).contiguous()
+        sort_s.append(_argsort_masks(part, kv, do_sort, alloc)[0])
+        mask_s.append(part[0])
+    return mask_s, sort_s
+
+
 # ---------------------------------------------------------------------------- rulebooks
 def get_indice_pairs(indices: torch.Tensor, batch_size: int, spatial_shape: List[int],
                      algo: ConvAlgo, ksize: List[int], stride: List[int], padding: List[int],
@@ -238,7 +252,14 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
                            transpose)
     geo = _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding,
                     dilation, transpose)
-    masks = [np.array([0xffffffff], dtype=np.uint32)]
+    is_split = algo == ConvAlgo.MaskSplitImplicitGemm
+    if is_split:
+        assert words == 1, "Not Implemented"                    # reference: ops.py:495
+        remain = kv - kv // 2
+        masks = [np.array([(1 << remain) - 1], dtype=np.uint32),
+                 np.array([((1 << (kv // 2)) - 1) << remain], dtype=np.uint32)]
+    else:
+        masks = [np.array([0xffffffff], dtype=np.uint32)]
     # per-offset pair counts are not consumed by the GEMM; kept for API shape
     indice_num_per_loc = torch.zeros((kv,), dtype=torch.int32, device=dev)
     if subm:
@@ -258,17 +279,26 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
                                               pair[1].data_ptr() if is_train and n_in else None,
                                               _ptr(pair_mask), _ptr(rows), ws.data_ptr(), ws.numel(),
                                               _stream()), "subm_rulebook")
+        pair_bwd = pair[1] if is_train else torch.Tensor()
+        if is_split:
+            with timer.record("gen_subm_inds_sort", _stream()):
+                mask_s, sort_s = _split_and_sort(pair_mask, masks, kv, do_sort, alloc)
+            return (indices, indice_num_per_loc, pair[0], pair_bwd, mask_s, [], sort_s, [], masks)
         with timer.record("gen_subm_inds_sort", _stream()):
             mask_argsort = _argsort_masks(pair_mask, kv, do_sort, alloc)
         argsort_view = mask_argsort[0]
         if rows is not None:
             argsort_view._spx_row_table = (pair[0].data_ptr(), rows)
-        pair_bwd = pair[1] if is_train else torch.Tensor()
         return (indices, indice_num_per_loc, pair[0], pair_bwd, [pair_mask[0]], [],
                 [argsort_view], [], masks)
     with timer.record("gen_conv_inds", _stream()):
         out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd = _conv_rulebook(
             geo, indices, n_in, kv, words, True, alloc)
+    if is_split:
+        with timer.record("gen_conv_inds_sort", _stream()):
+            mf, sf = _split_and_sort(mask_fwd, masks, kv, do_sort, alloc)
+            mb, sb = _split_and_sort(mask_bwd, masks, kv, do_sort, alloc) if is_train else ([], [])
+        return (out_inds, indice_num_per_loc, pair_fwd, pair_bwd, mf, mb, sf, sb, masks)
     with timer.record("gen_conv_inds_sort", _stream()):
         argsort_fwd = _argsort_masks(mask_fwd, kv, do_sort, alloc)
         if is_train:
@@ -369,6 +399,11 @@ def implicit_gemm(features: torch.Tensor, filters: torch.Tensor, pair_fwd: torch
     kv, c_in, c_out = _check_filter(features, filters)
     assert features.shape[1] == c_in, "channel size mismatch"
     n_in, n_out = features.shape[0], int(num_activate_out)
+    n_splits = len(pair_mask_fwd_splits) if isinstance(pair_mask_fwd_splits, (list, tuple)) else 1
+    if n_splits > 1:
+        return _implicit_gemm_splits(features, filters, pair_fwd, pair_mask_fwd_splits,
+                                     mask_argsort_fwd_splits, n_out, is_train, timer, bias, act_alpha,
+                                     act_type, output_add, output_dtype)
     mask = _first(pair_mask_fwd_splits)
     argsort = _first(mask_argsort_fwd_splits)
     is_int8 = features.dtype == torch.int8
@@ -408,6 +443,40 @@ def implicit_gemm(features: torch.Tensor, filters: torch.Tensor, pair_fwd: torch
     return out, mask_output, MASK_WIDTH
 
 
+def _implicit_gemm_splits(features, filters, pair_fwd, mask_splits, argsort_splits, n_out, is_train, timer,
+                          bias, act_alpha, act_type, output_add, output_dtype):
+    """ConvAlgo.MaskSplitImplicitGemm forward: one kernel pass per mask split (each visits only its
+    own offsets, rows in that split's sorted order), partial outputs summed, bias / activation after
+    the last split (the reference fuses them into the last pass, ``convops.py:2196-2234``)."""
+    lib = _lib()
+    if features.dtype == torch.int8:
+        raise NotImplementedError("int8 + MaskSplitImplicitGemm: use ConvAlgo.MaskImplicitGemm")
+    kv, c_in, c_out = _check_filter(features, filters)
+    n_in = features.shape[0]
+    words = (kv + 31) // 32
+    out = None
+    tile_masks = []
+    for mask, argsort in zip(mask_splits, argsort_splits):
+        tiles = _tile_tables(pair_fwd, mask, argsort, n_out, kv, owner=argsort) if n_out else None
+        d = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, pair_fwd, mask, argsort, tiles=tiles)
+        part = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
+        with timer.record("implicit_gemm", _stream()):
+            _cabi.check(lib.spx_implicit_gemm_fwd(ctypes.byref(d), _ptr(features), _ptr(filters), _ptr(part),
+                                                  None, _cabi.SPX_ACT_NONE, 0.0, None, _stream()),
+                        "implicit_gemm_fwd(split)")
+        out = part if out is None else out.add_(part)
+        if tiles is not None:
+            tile_masks.append(tiles[1].view(1, -1, words))
+    if (bias is not None or _act_code(act_type) != _cabi.SPX_ACT_NONE) and n_out:
+        bias_add_act_inplace(out, bias, act_type, act_alpha)
+    if output_add is not None:
+        out = out + output_add
+    if output_dtype is not None and output_dtype != out.dtype:
+        out = out.to(output_dtype)
+    mask_output = torch.cat(tile_masks, 0) if (is_train and tile_masks) else torch.Tensor()
+    return out, mask_output, MASK_WIDTH
+
+
 def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: torch.Tensor,
                            pair_fwd: torch.Tensor, pair_bwd: torch.Tensor,
                            pair_mask_fwd_splits: List[torch.Tensor],
@@ -429,6 +498,19 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         out_bp = out_bp.to(features.dtype)
     kv, c_in, c_out = _check_filter(features, filters)
     n_in, n_out = features.shape[0], out_bp.shape[0]
+    n_splits = len(pair_mask_fwd_splits) if isinstance(pair_mask_fwd_splits, (list, tuple)) else 1
+    if n_splits > 1:
+        # MaskSplitImplicitGemm: gradients are sums over the splits (each split only visits its offsets)
+        din = dfilters = None
+        for j in range(n_splits):
+            bwd_m = [pair_mask_bwd_splits[j]] if pair_mask_bwd_splits else []
+            bwd_s = [mask_argsort_bwd_splits[j]] if mask_argsort_bwd_splits else []
+            di, dw = implicit_gemm_backward(features, filters, out_bp, pair_fwd, pair_bwd,
+                                            [pair_mask_fwd_splits[j]], bwd_m, [mask_argsort_fwd_splits[j]],
+                                            bwd_s, None, masks, mask_width, is_subm, timer, fp32_accum)
+            din = di if din is None else din.add_(di)
+            dfilters = dw if dfilters is None else dfilters.add_(dw)
+        return din, dfilters
     din = torch.empty_like(features)
     dfilters = torch.empty_like(filters)
     mask_fwd, argsort_fwd = _first(pair_mask_fwd_splits), _first(mask_argsort_fwd_splits)

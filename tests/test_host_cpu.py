@@ -116,3 +116,47 @@ def test_output_size_helpers():
     assert ops.get_deconv_output_size([4, 4], [3, 3], [2, 2], [1, 1], [1, 1], [1, 1]) == [8, 8]
     with pytest.raises(ValueError):
         ops.get_deconv_output_size([4], [-1], [1], [0], [1], [0])
+
+
+def test_saved_weight_layout_hook_converts_legacy_checkpoints():
+    """SPCONV_SAVED_WEIGHT_LAYOUT = RSKC / RSCK checkpoints load as KRSC (spconv/pytorch/conv.py:648-683)"""
+    import torch
+    import spconv_b200.pytorch as spconv
+    from spconv_b200 import constants
+    src = spconv.SparseConv3d(4, 6, [3, 2, 1], bias=False, record_voxel_count=True)
+    w = src.weight.detach().clone()                                   # [6, 3, 2, 1, 4]
+    try:
+        for layout, perm in (("RSKC", (1, 2, 3, 0, 4)), ("RSCK", (1, 2, 3, 4, 0)), ("KRSC", (0, 1, 2, 3, 4)), ("", (0, 1, 2, 3, 4))):
+            constants.SAVED_WEIGHT_LAYOUT = layout
+            dst = spconv.SparseConv3d(4, 6, [3, 2, 1], bias=False, record_voxel_count=True)
+            dst.load_state_dict({"weight": w.permute(*perm).contiguous()})      # no voxel-count buffer: supplied
+            assert torch.equal(dst.weight, w), layout
+            assert dst.get_max_num_voxels() is not None
+    finally:
+        constants.SAVED_WEIGHT_LAYOUT = ""
+
+
+def test_fuse_bn_weights_equals_dense_conv_then_bn():
+    """eval-time BN folding (example/fuse_bn_act.py:36-56) on the KRSC filter"""
+    import torch
+    import spconv_b200.pytorch as spconv
+    torch.manual_seed(0)
+    conv = torch.nn.Conv3d(4, 6, 3, bias=True).eval()
+    bn = torch.nn.BatchNorm3d(6).eval()
+    with torch.no_grad():
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-1, 1)
+    krsc = conv.weight.detach().permute(0, 2, 3, 4, 1).contiguous()
+    wf, bf = spconv.fuse_bn_weights(krsc, conv.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
+                                    bn.weight.detach(), bn.bias.detach())
+    x = torch.randn(2, 4, 8, 8, 8)
+    got = torch.nn.functional.conv3d(x, wf.detach().permute(0, 4, 1, 2, 3), bf.detach())
+    assert (bn(conv(x)) - got).abs().max() < 1e-5
+    # no conv bias / no affine
+    wf2, bf2 = spconv.fuse_bn_weights(krsc, None, bn.running_mean, bn.running_var, bn.eps, None, None)
+    ref2 = (torch.nn.functional.conv3d(x, conv.weight, None) - bn.running_mean.view(1, -1, 1, 1, 1)) \
+        * torch.rsqrt(bn.running_var + bn.eps).view(1, -1, 1, 1, 1)
+    got2 = torch.nn.functional.conv3d(x, wf2.detach().permute(0, 4, 1, 2, 3), bf2.detach())
+    assert (ref2 - got2).abs().max() < 1e-5

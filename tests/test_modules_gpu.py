@@ -134,3 +134,84 @@ def test_training_step_matches_fp32_oracle_and_amp(oracle, cuda_dev):
     dout = (2.0 / ref.size) * ref
     _, ref_dw = oracle.indice_conv_backward(f16, w, dout, p, n, False, True)
     assert rel_l2(layer.weight.grad.cpu().numpy(), ref_dw) < 3e-2
+
+
+def test_fused_bn_act_block_equals_unfused(cuda_dev):
+    """north_star "fused BN/act": conv -> BatchNorm1d -> ReLU folded into ONE kernel launch per layer
+    (weights + bias folded on the host, bias + activation in the GEMM epilogue); reference recipe
+    example/fuse_bn_act.py:36-86"""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(4)
+    shape = [20, 20, 20]
+    feats, inds = random_cloud(rng, shape, [2500], 32)
+    net = spconv.SparseSequential(
+        spconv.SubMConv3d(32, 32, 3, bias=False, indice_key="a"), torch.nn.BatchNorm1d(32), torch.nn.ReLU(),
+        spconv.SparseConv3d(32, 64, 3, 2, 1, bias=True), torch.nn.BatchNorm1d(64), torch.nn.LeakyReLU(0.1),
+        spconv.SubMConv3d(64, 64, 3, bias=False, indice_key="b"), torch.nn.BatchNorm1d(64),
+    ).to(cuda_dev)
+    with torch.no_grad():
+        for m in net:
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.uniform_(-0.5, 0.5)
+                m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.5, 0.5)
+    net.eval()
+    fused = spconv.fuse_bn_act_sequential(net)
+    assert len(fused) == 3 and all(isinstance(m, spconv.SparseConvolution) for m in fused)
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev), torch.from_numpy(inds).to(cuda_dev), shape, 1)
+    with torch.no_grad():
+        ref = net(x)
+        ops.launch_count(reset=True)
+        got = fused(x)
+    assert torch.equal(ref.indices, got.indices)
+    assert (ref.features - got.features).abs().max() < 1e-4 * max(1.0, float(ref.features.abs().max()))
+
+
+@pytest.mark.parametrize("subm", [True, False])
+def test_mask_split_implicit_gemm_is_a_real_split(subm, oracle, cuda_dev):
+    """ConvAlgo.MaskSplitImplicitGemm (spconv/pytorch/ops.py:494-503): two mask splits (low / high
+    offsets), each sorted on its own, one kernel pass per split; results equal the unsplit algo."""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(21)
+    shape = [20, 22, 18]
+    feats, inds = random_cloud(rng, shape, [2600], 32)
+    d_inds = torch.from_numpy(inds).to(cuda_dev)
+    k, s, p = ([3] * 3, [1] * 3, [1] * 3) if subm else ([3] * 3, [2] * 3, [1] * 3)
+    res = ops.get_indice_pairs_implicit_gemm(d_inds, 1, shape, ConvAlgo.MaskSplitImplicitGemm, k, s, p, [1] * 3,
+                                             [0] * 3, subm, False, is_train=True)
+    out_inds, _, pair_fwd, pair_bwd, mask_f, mask_b, sort_f, sort_b, masks = res
+    assert len(mask_f) == 2 and len(sort_f) == 2 and len(masks) == 2
+    assert int(masks[0][0]) == (1 << 14) - 1 and int(masks[1][0]) == ((1 << 13) - 1) << 14
+    o, pairs, num = oracle.get_indice_pairs(inds, 1, shape, k, s, p, [1] * 3, [0] * 3, subm)
+    tabs = oracle.implicit_gemm_tables(pairs, num, inds.shape[0], o.shape[0], subm)
+    full = tabs["mask_fwd_unsorted"][:, 0]
+    for j in range(2):
+        want = full & masks[j][0]
+        order = np.argsort(want, kind="stable")
+        assert np.array_equal(sort_f[j].cpu().numpy(), order)
+        assert np.array_equal(mask_f[j].cpu().numpy().view(np.uint32)[:, 0], want[order])
+    # module level: same weights, split vs unsplit
+    cls = spconv.SubMConv3d if subm else spconv.SparseConv3d
+    args = (32, 48, 3) if subm else (32, 48, 3, 2, 1)
+    a = cls(*args, bias=True, algo=ConvAlgo.MaskImplicitGemm).to(cuda_dev).half()
+    b = cls(*args, bias=True, algo=ConvAlgo.MaskSplitImplicitGemm).to(cuda_dev).half()
+    b.load_state_dict(a.state_dict())
+    outs = []
+    for m in (a, b):
+        xf = torch.from_numpy(feats).to(cuda_dev).half().requires_grad_(True)
+        y = m(spconv.SparseConvTensor(xf, d_inds, shape, 1))
+        y.features.float().square().mean().backward()
+        outs.append((y.features.detach().float(), xf.grad.float(), m.weight.grad.float(), m.bias.grad.float()))
+    for u, v in zip(*outs):
+        assert rel_l2(v.cpu().numpy(), u.cpu().numpy()) < 5e-3
+    # inference path with fused bias + activation after the last split
+    a.eval(), b.eval()
+    a.act_type = b.act_type = spconv.Activation.ReLU
+    with torch.no_grad():
+        x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev).half(), d_inds, shape, 1)
+        ya, yb = a(x).features.float(), b(x).features.float()
+    assert (ya >= 0).all() and rel_l2(yb.cpu().numpy(), ya.cpu().numpy()) < 5e-3
