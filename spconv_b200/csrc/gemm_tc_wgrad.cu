@@ -14,8 +14,12 @@
 //     with fp32 workspaces, spconv/csrc/sparse/convops.py:1236-1243, :2421-2436).
 // Roles: warps 0-3 drain only, 4-11 gather producers (16-byte cp.async, 16 tile rows per warp;
 // they join the drain at the end), 12 MMA issuer, 13 tile feeder (index-block ring + per-tile
-// group sets).  Tiles are assigned statically (chunk, chunk + chunks, ...) so the summation
-// order of dW -- and with it the result -- is reproducible bit for bit.
+// group sets).  Tiles are assigned STATICALLY so the summation order of dW -- and with it the
+// result -- is reproducible bit for bit, but not round-robin: the schedule records list the tiles
+// by decreasing offset count, and CTA c takes records c, 2C-1-c, 2C+c, 4C-1-c, ... (a snake over
+// rows of C = chunks records).  Every CTA then holds one tile of every cost rank, which is LPT
+// list scheduling without a run-time counter (round-robin over the unsorted tiles left the
+// slowest CTA ~15 us behind the median on the 100 k-voxel cloud).
 #include "gemm.cuh"
 #include <stdlib.h>
 
@@ -41,6 +45,7 @@ struct WgParams {
     int64_t rows;
     const int32_t *tile_table;   // [tiles][kv+1][128]
     const uint32_t *tile_mask;   // [tiles][words]
+    const int32_t *sched_rec;    // [tiles][TT_REC_INTS] {tile, mask[4]}: tiles by decreasing offset count (gemm.cuh)
     int kv, words, c_in;
     float *partial; int64_t partial_stride;
     long long *dbg_ts;           // optional [8][2048] clock64 stamps of CTA (0,0) (SPX_TC_TRACE)
@@ -79,6 +84,16 @@ __device__ __forceinline__ void wg_load_tile_mask(const uint32_t *__restrict__ t
                                                   uint32_t (&out)[4]) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) out[w] = w < words ? __ldg(tile_mask + tile * words + w) : 0u;
+}
+
+// record visited by CTA `chunk` at step i (snake order over the cost-sorted schedule records)
+__device__ __forceinline__ int64_t wg_rec_index(int64_t i, int chunk, int chunks) {
+    return i * chunks + ((i & 1) ? (chunks - 1 - chunk) : chunk);
+}
+__device__ __forceinline__ void wg_load_rec(const int32_t *__restrict__ rec, int64_t r, int64_t &tile, uint32_t (&m)[4]) {
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(rec + r * TT_REC_INTS));
+    const int b = __ldg(rec + r * TT_REC_INTS + 4);
+    tile = a.x; m[0] = (uint32_t)a.y; m[1] = (uint32_t)a.z; m[2] = (uint32_t)a.w; m[3] = (uint32_t)b;
 }
 
 __device__ __forceinline__ long long wg_global_ns() {
@@ -234,17 +249,15 @@ tc_wgrad_kernel(const WgParams p) {
             m[0] = r[1]; m[1] = r[2]; m[2] = r[3]; m[3] = r[4];
             return r[0];
         };
-        int64_t tile = chunk;
         int cur_slot = 0; uint32_t cur_use = 0;          // ring position of the tile being gathered
         uint32_t tm[4] = {0, 0, 0, 0}, tm1[4] = {0, 0, 0, 0};
         uint32_t act = 0;
-        if (tile < num_tiles) {
+        if (wg_rec_index(0, chunk, chunks) < num_tiles) {
             act = read_slot(0, 0u, tm);
             if (act) issue_b(idx_block(0));
         }
-        for (; tile < num_tiles; tile += chunks) {
-            const int64_t next = tile + chunks;
-            const bool has_next = next < num_tiles;
+        for (int64_t step = 0; wg_rec_index(step, chunk, chunks) < num_tiles; ++step) {
+            const bool has_next = wg_rec_index(step + 1, chunk, chunks) < num_tiles;
             int nxt_slot = cur_slot + 1; uint32_t nxt_use = cur_use;
             if (nxt_slot == nring) { nxt_slot = 0; ++nxt_use; }
             uint32_t act_next = 0;
@@ -301,15 +314,16 @@ tc_wgrad_kernel(const WgParams p) {
         const int nring = p.idx_bufs;
         int slot = 0; uint32_t use = 0;
         uint32_t mw[4] = {0, 0, 0, 0};
-        int64_t i = 0;
-        for (int64_t tile = chunk; tile < num_tiles; tile += chunks, ++i) {
-            if ((i & 31) == 0) {
-                const int64_t t = tile + (int64_t)lane * chunks;
-                if (t < num_tiles) wg_load_tile_mask(p.tile_mask, t, p.words, mw);
+        int64_t mtile = 0;
+        for (int64_t i = 0; wg_rec_index(i, chunk, chunks) < num_tiles; ++i) {
+            if ((i & 31) == 0) {                         // the next 32 schedule records, one per lane
+                const int64_t r = wg_rec_index(i + lane, chunk, chunks);
+                if (r < num_tiles) wg_load_rec(p.sched_rec, r, mtile, mw);
             }
             uint32_t tm[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) tm[w] = __shfl_sync(0xffffffffu, mw[w], (int)(i & 31));
+            const int64_t tile = __shfl_sync(0xffffffffu, mtile, (int)(i & 31));
             const uint32_t act = active_groups(tm, gmask, ng, p.words);
             mbar_wait(&idx_empty[slot], (use & 1u) ^ 1u);
             if (lane == 0) {
@@ -332,18 +346,19 @@ tc_wgrad_kernel(const WgParams p) {
         int64_t nb = 0;
         uint32_t used = 0;
         int nst = 0, ntile = 0;
-        int64_t tile = chunk;
         uint32_t tm[4] = {0, 0, 0, 0};
-        if (tile < num_tiles) wg_load_tile_mask(p.tile_mask, tile, p.words, tm);
+        int64_t tile_unused = 0;
+        if (wg_rec_index(0, chunk, chunks) < num_tiles)
+            wg_load_rec(p.sched_rec, wg_rec_index(0, chunk, chunks), tile_unused, tm);
         // both operands are MN-major: LBO = distance between 128-row atoms, SBO = 8 rows
         const uint64_t a_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
         const uint64_t b_hi = smem_desc_hi((uint32_t)(WG_TILE * SPAN_D), 8u * SPAN_D, SPAN_D);
         const uint32_t a_step16 = (uint32_t)(p.rows_per_kstep * p.span_x) >> 4;
         const uint32_t b_step16 = (uint32_t)(p.rows_per_kstep * SPAN_D) >> 4;
-        for (; tile < num_tiles; tile += chunks) {
-            const int64_t next = tile + chunks;
+        for (int64_t step = 0; wg_rec_index(step, chunk, chunks) < num_tiles; ++step) {
+            const int64_t next = wg_rec_index(step + 1, chunk, chunks);
             uint32_t tm_next[4] = {0, 0, 0, 0};
-            if (next < num_tiles) wg_load_tile_mask(p.tile_mask, next, p.words, tm_next);
+            if (next < num_tiles) wg_load_rec(p.sched_rec, next, tile_unused, tm_next);
             const uint32_t act = active_groups(tm, gmask, ng, p.words);
             if (act) {
                 const int bb = (int)(nb & 1);
@@ -533,6 +548,7 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     if (chunks < 1) chunks = 1;
     pl.chunks = chunks;
     p.rows = a.n_out; p.tile_table = a.tile_table; p.tile_mask = a.tile_mask;
+    p.sched_rec = a.tile_table + tt_blocks_elems(tiles, a.kv);
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.c_in = a.c_in;
     p.x = (const uint8_t *)a.x; p.d = (const uint8_t *)a.dout;
     p.partial_stride = (int64_t)a.kv * a.c_in * a.c_out;

@@ -15,6 +15,14 @@
 //             memory, then one global atomic per distinct (digit, block) cell.
 // The first pass reads the masks with an implicit iota payload, the last pass writes the sorted
 // masks back in place (thrust semantics) and the argsort.
+//
+// Default path ("onesweep"): ONE kernel per pass.  The digit totals of every pass do not depend on
+// the key order, so a single histogram kernel counts all passes up front; a pass kernel then needs
+// only the number of equal digits in the tiles BEFORE its own, which it gets by decoupled
+// look-back over per-tile status words {count | flag} (tile ids are drawn from an atomic ticket, so
+// every predecessor is already running and publishes its aggregate before it waits on anyone).
+// 1 + passes launches instead of 1 + 2 * passes; the legacy two-kernel passes stay selectable with
+// debug bit 64 (spx_debug_configure) for A/B runs.
 #include "common.cuh"
 
 namespace spx {
@@ -181,9 +189,153 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     }
 }
 
+
+// ------------------------------------------------------------------ onesweep path
+constexpr uint32_t OS_FLAG_AGG = 1u << 30;      // status word = flag | value (value < 2^30)
+constexpr uint32_t OS_FLAG_PREFIX = 2u << 30;
+constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1u;
+constexpr int OS_MAX_PASSES = 4;
+
+// digit histograms of ALL passes in one sweep over the keys: hist[pass][digit]
+__global__ void __launch_bounds__(RS_THREADS)
+os_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int passes, int *__restrict__ hist) {
+    __shared__ int h[OS_MAX_PASSES][RS_BINS];
+    for (int i = threadIdx.x; i < OS_MAX_PASSES * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int64_t i = base + j * RS_THREADS + threadIdx.x;
+        if (i < n) {
+            const uint32_t k = keys[i];
+            for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k >> (p * RS_BITS)) & (RS_BINS - 1)], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RS_BINS; i += RS_THREADS) {
+        const int v = (&h[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+__device__ __forceinline__ uint32_t os_load_status(const uint32_t *p) {
+    return *reinterpret_cast<const volatile uint32_t *>(p);          // L2 (never a stale L1 line)
+}
+
+// One radix pass.  status: [tiles][RS_BINS] words, zero before the launch; ticket: one counter.
+template <bool IOTA_IN>
+__global__ void __launch_bounds__(RS_THREADS)
+os_pass_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
+               const int *__restrict__ hist, uint32_t *__restrict__ status, int *__restrict__ ticket,
+               uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
+    __shared__ int digit_base[RS_BINS];             // global start of each digit + keys of earlier tiles
+    __shared__ int warp_cnt[RS_WARPS][RS_BINS];
+    __shared__ int scan_tmp[RS_WARPS];
+    __shared__ int tile_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) tile_s = atomicAdd(ticket, 1);
+    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
+    // exclusive scan of the 512 digit totals (digit d = q * 256 + tid)
+    int my_total[RS_BINS / RS_THREADS];
+#pragma unroll
+    for (int q = 0; q < RS_BINS / RS_THREADS; ++q) my_total[q] = __ldg(hist + q * RS_THREADS + tid);
+    __syncthreads();
+    const int tile = tile_s;
+    int run = 0;
+#pragma unroll
+    for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+        int v = my_total[q], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) scan_tmp[warp] = incl;
+        __syncthreads();
+        int wbase = 0, all = 0;
+        for (int w = 0; w < RS_WARPS; ++w) { if (w < warp) wbase += scan_tmp[w]; all += scan_tmp[w]; }
+        digit_base[q * RS_THREADS + tid] = run + wbase + incl - v;
+        run += all;
+        __syncthreads();
+    }
+    // stable rank inside the tile: warp w owns keys [w*128, w*128+128), 4 rounds of 32
+    const int64_t tile_base = (int64_t)tile * RS_TILE + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS];
+    int32_t val[RS_ITEMS];
+    int rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = tile_base + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0xffffffffu;
+        val[r] = ok ? (IOTA_IN ? (int32_t)i : vals_in[i]) : -1;
+        const int d = ok ? (int)((key[r] >> shift) & (RS_BINS - 1)) : RS_BINS;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        int old = 0;
+        if (ok && lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per-digit: warp bases (exclusive over warps) and the tile's count, published at once for both
+    // digits of this thread (nobody must wait for a look-back of ours to see our aggregate) ...
+    int cnt[RS_BINS / RS_THREADS];
+#pragma unroll
+    for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+        const int d = q * RS_THREADS + tid;
+        int acc = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const int c = warp_cnt[w][d]; warp_cnt[w][d] = acc; acc += c; }
+        cnt[q] = acc;
+        atomicExch(status + (int64_t)tile * RS_BINS + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | (uint32_t)acc);
+    }
+    // ... then the look-back: sum the aggregates of the tiles before this one until a tile that
+    // already knows its inclusive prefix, and publish ours
+    if (tile > 0) {
+#pragma unroll
+        for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+            const int d = q * RS_THREADS + tid;
+            uint32_t excl = 0;
+            for (int t = tile - 1; t >= 0; --t) {
+                const uint32_t *other = status + (int64_t)t * RS_BINS + d;
+                uint32_t w = os_load_status(other);
+                uint32_t spins = 0;
+                while ((w >> 30) == 0u) {
+                    if (++spins > (1u << 22)) {       // a protocol bug must become an error, not a hung GPU
+                        printf("spconv_b200: radix look-back timed out (tile %d digit %d waits on tile %d)\n", tile, d, t);
+                        __trap();
+                    }
+                    w = os_load_status(other);
+                }
+                excl += w & OS_VALUE_MASK;
+                if (w & OS_FLAG_PREFIX) break;
+            }
+            atomicExch(status + (int64_t)tile * RS_BINS + d, OS_FLAG_PREFIX | (excl + (uint32_t)cnt[q]));
+            digit_base[d] += (int)excl;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = tile_base + r * 32 + lane;
+        if (i < n) {
+            const int d = (int)((key[r] >> shift) & (RS_BINS - 1));
+            const int pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
 size_t radix_argsort_workspace_bytes(int64_t n) {
     const int64_t nblk = div_up64(n > 0 ? n : 1, RS_TILE);
-    return 4 * align_up((size_t)n * 4, 256) + 2 * align_up((size_t)RS_BINS * nblk * 4, 256) + align_up(RS_BINS * 4, 256) + 1024;
+    // legacy path: 2 count matrices + totals; onesweep: hist + tickets + per-pass status words (they share)
+    const size_t legacy = 2 * align_up((size_t)RS_BINS * nblk * 4, 256) + align_up(RS_BINS * 4, 256);
+    const size_t sweep = align_up((size_t)(OS_MAX_PASSES * RS_BINS + 64) * 4, 256) +
+                         align_up((size_t)OS_MAX_PASSES * nblk * RS_BINS * 4, 256);
+    return 4 * align_up((size_t)n * 4, 256) + (legacy > sweep ? legacy : sweep) + 1024;
 }
 
 // keys: mask [n] (sorted in place on return), argsort [n] out.  Returns 0 / error code.
@@ -196,14 +348,44 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
     uint32_t *keys_b = ws.take<uint32_t>(n);
     int32_t *vals_b = ws.take<int32_t>(n);
     const int nblk = (int)div_up64(n, RS_TILE);
-    int *counts_ab[2] = {ws.take<int>((size_t)RS_BINS * nblk), ws.take<int>((size_t)RS_BINS * nblk)};
-    int *totals = ws.take<int>(RS_BINS);
-    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 32) key_bits = 32;
     const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
     const uint32_t *kin = mask;
     const int32_t *vin = nullptr;
+    if (!(runtime_cfg().debug & 64)) {
+        // ---- onesweep: memset(scratch) + histogram of all passes + one kernel per pass
+        const size_t head_ints = (size_t)OS_MAX_PASSES * RS_BINS + 64;        // hist[4][512] + tickets
+        int *head = ws.take<int>(head_ints);
+        uint32_t *status = ws.take<uint32_t>((size_t)passes * nblk * RS_BINS);
+        SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+        const size_t clear_bytes = (size_t)((char *)(status + (size_t)passes * nblk * RS_BINS) - (char *)head);
+        SPX_CHECK_CUDA(cudaMemsetAsync(head, 0, clear_bytes, stream));
+        int *hist = head, *tickets = head + OS_MAX_PASSES * RS_BINS;
+        os_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, passes, hist);
+        SPX_CHECK_LAUNCH("os_hist_kernel");
+        for (int pass = 0; pass < passes; ++pass) {
+            const bool last = pass == passes - 1;
+            uint32_t *kout = (pass & 1) ? keys_b : keys_a;
+            int32_t *vout = (pass & 1) ? vals_b : vals_a;
+            if (last && pass > 0) { kout = mask; vout = argsort; }
+            uint32_t *st = status + (size_t)pass * nblk * RS_BINS;
+            if (pass == 0)
+                os_pass_kernel<true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, pass * RS_BITS, hist + pass * RS_BINS, st, tickets + pass, kout, vout);
+            else
+                os_pass_kernel<false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, pass * RS_BITS, hist + pass * RS_BINS, st, tickets + pass, kout, vout);
+            SPX_CHECK_LAUNCH("os_pass_kernel");
+            kin = kout; vin = vout;
+        }
+        if (passes == 1) {
+            SPX_CHECK_CUDA(cudaMemcpyAsync(mask, keys_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+            SPX_CHECK_CUDA(cudaMemcpyAsync(argsort, vals_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        }
+        return 0;
+    }
+    int *counts_ab[2] = {ws.take<int>((size_t)RS_BINS * nblk), ws.take<int>((size_t)RS_BINS * nblk)};
+    int *totals = ws.take<int>(RS_BINS);
+    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
     rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, 0, nblk, counts_ab[0]);
     SPX_CHECK_LAUNCH("rs_hist_kernel");
     for (int pass = 0; pass < passes; ++pass) {

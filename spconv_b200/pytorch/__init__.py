@@ -13,3 +13,4 @@ from .modules import (RemoveGrid, SparseBatchNorm, SparseIdentity, SparseModule,
 from .pool import (SparseAvgPool1d, SparseAvgPool2d, SparseAvgPool3d, SparseGlobalAvgPool,  # noqa: F401
                    SparseGlobalMaxPool, SparseMaxPool1d, SparseMaxPool2d, SparseMaxPool3d, SparseMaxPool4d)
 from .utils_fuse import (fuse_act, fuse_bn, fuse_bn_act_sequential, fuse_bn_weights)  # noqa: F401
+from . import quantized  # noqa: F401

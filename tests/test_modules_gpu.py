@@ -215,3 +215,43 @@ def test_mask_split_implicit_gemm_is_a_real_split(subm, oracle, cuda_dev):
         x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev).half(), d_inds, shape, 1)
         ya, yb = a(x).features.float(), b(x).features.float()
     assert (ya >= 0).all() and rel_l2(yb.cpu().numpy(), ya.cpu().numpy()) < 5e-3
+
+
+@pytest.mark.parametrize("subm", [True, False])
+def test_quantized_sparse_conv_hookup(subm, oracle, cuda_dev):
+    """static int8 module: per-channel scale derivation of the reference
+    (spconv/pytorch/quantization/quantized/conv.py:368-377) + the int8 kernel; exact against the
+    numpy formula of test/test_all_algo.py:272-287, close to the float layer"""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.pytorch import quantized as Q
+    rng = np.random.default_rng(8)
+    shape = [20, 20, 20]
+    feats, inds = random_cloud(rng, shape, [2500], 32)
+    cls, args = (spconv.SubMConv3d, (32, 64, 3)) if subm else (spconv.SparseConv3d, (32, 64, 3, 2, 1))
+    fconv = cls(*args, bias=True).to(cuda_dev).eval()
+    fconv.act_type = spconv.Activation.ReLU
+    x = spconv.SparseConvTensor(torch.from_numpy(feats).to(cuda_dev), torch.from_numpy(inds).to(cuda_dev), shape, 1)
+    out_scale = Q.calibrate_output_scale(fconv, x)
+    qconv = Q.QuantizedSparseConv.from_float(fconv, out_scale)
+    in_scale = 1.0 / 127.0
+    xq = Q.quantize_tensor(x, in_scale)
+    with torch.no_grad():
+        yq = qconv(xq)
+        yf = fconv(x)
+    assert yq.features.dtype == torch.int8 and yq.int8_scale == out_scale
+    # exact vs the reference formula
+    s = [1] * 3 if subm else [2] * 3
+    o, pairs, num = oracle.get_indice_pairs(inds, 1, shape, [3] * 3, s, [1] * 3, [1] * 3, [0] * 3, subm)
+    ch_scale = (in_scale * qconv.weight_scales.cpu().numpy()) / out_scale
+    ref = oracle.int8_conv_forward(xq.features.cpu().numpy(), qconv.weight.cpu().numpy(), pairs, num, o.shape[0], subm,
+                                   ch_scale.astype(np.float32), (qconv.bias.cpu().numpy() / out_scale).astype(np.float32),
+                                   relu=True, out_int8=True)
+    got = yq.features.cpu().numpy()
+    assert np.array_equal(yq.indices.cpu().numpy(), o)
+    # rint at exact .5 ties can differ by fp32 evaluation order: allow a handful of off-by-one
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())
+    # close to the float layer (quantisation noise only)
+    deq = Q.dequantize_tensor(yq).features
+    err = (deq - yf.features).abs().max() / yf.features.abs().max()
+    assert float(err) < 0.05, float(err)
