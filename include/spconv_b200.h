@@ -22,6 +22,8 @@
  *                                                    spconv/csrc/sparse/convops.py:1504-2071
  *   spx_bias_act_inplace
  *        <- InferenceOps.bias_add_act_inplace        spconv/csrc/sparse/inference.py:166-252
+ *   spx_point2voxel_stage1 / _stage2
+ *        <- SpconvOps.point2voxel_cuda               spconv/csrc/sparse/all.py:1349-1490
  *   spx_indice_pool_fwd / spx_indice_pool_bwd / spx_global_pool_rearrange
  *        <- SpconvOps.maxpool_forward / maxpool_backward / maxpool_implicit_gemm_forward /
  *           maxpool_implicit_gemm_backward / avgpool_implicit_gemm_forward / _backward /
@@ -231,6 +233,38 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
 /* x[r, j] = act(x[r, j] + bias[j])   in place; bias may be NULL */
 int spx_bias_act_inplace(void *x, const void *bias, int64_t rows, int cols, int dtype, int act,
                          float act_alpha, spx_stream_t stream);
+
+/* ------------------------------------------------------------------ point cloud -> voxels */
+
+/*
+ * Replaces SpconvOps.point2voxel_cuda / Point2Voxel (spconv/csrc/sparse/all.py:1349-1490,
+ * spconv/csrc/sparse/pointops.py:120-490) with the deterministic semantics of the reference's CPU
+ * implementation (Point2VoxelCPU, pointops.py:589-695): voxel id = rank of the voxel's first point
+ * in input order; voxels beyond max_voxels are dropped; a voxel keeps its first
+ * max_points_per_voxel points in input order.
+ *   points [N, num_features] fp32 (device), the first ndim features are coordinates (x, y, z, ..);
+ *   vsize / grid_size / coors_range are HOST arrays in the internal axis order that
+ *   calc_meta_data produces (zyx != 0: axis j reads point feature ndim-1-j);  coors_range holds the
+ *   ndim lower bounds first.
+ * Stage 1 hashes and ranks the voxels and returns their number (host sync, as the reference's
+ * sliced return tensors require): *num_voxels = min(total, max_voxels).  Stage 2 (same untouched
+ * workspace) fills
+ *   voxels [>= num_voxels, max_points, num_features] (unused slots are left as the caller set them,
+ *          or receive the voxel mean when empty_mean != 0),  indices [>= num_voxels, ndim],
+ *   num_per_voxel [>= num_voxels],  pc_voxel_id [N] int64 (-1 = no voxel).
+ */
+size_t spx_point2voxel_workspace_size(int64_t num_points, int ndim);
+int spx_point2voxel_stage1(const float *points, int64_t N, int num_features, int ndim, int zyx,
+                           const float *vsize_host, const int *grid_size_host,
+                           const float *coors_range_host, int64_t max_voxels, int64_t *num_voxels_host,
+                           int64_t *total_voxels_host, void *workspace, size_t workspace_bytes,
+                           spx_stream_t stream);
+int spx_point2voxel_stage2(const float *points, int64_t N, int num_features, int ndim, int zyx,
+                           const float *vsize_host, const int *grid_size_host,
+                           const float *coors_range_host, int64_t num_voxels, int64_t total_voxels,
+                           int max_points_per_voxel, int empty_mean, float *voxels, int32_t *indices,
+                           int32_t *num_per_voxel, int64_t *pc_voxel_id, void *workspace,
+                           size_t workspace_bytes, spx_stream_t stream);
 
 /* ------------------------------------------------------------------ pooling on the rulebook */
 

@@ -10,6 +10,8 @@ The reference's CPU implementation of this path is plain C++ held in Python f-st
 * ``spconv/csrc/sparse/gather.py:30-86``      ``GatherCPU`` (``gather`` / ``scatter_add``)
 * ``spconv/csrc/sparse/maxpool.py:590-700``   ``IndiceMaxPoolCPU`` (``forward`` / ``backward`` /
   ``global_pool_rearrange``)
+* ``spconv/csrc/sparse/pointops.py:42-88,589-695`` ``Point2VoxelCommon::calc_meta_data`` and
+  ``Point2VoxelCPU::point_to_voxel_static`` (+ the ``empty_mean`` variant)
 
 ``pccm`` / ``cumm`` / ``ccimport`` are not installable here (no network), so the reference's own
 build cannot run.  This script instead *executes the reference's generator methods* against a
@@ -44,7 +46,8 @@ GEN_HDR = os.path.join(OUT_DIR, "spconv_ref_gen.h")
 LIB = os.path.join(OUT_DIR, "libspconv_ref.so")
 SHIM = os.path.join(HERE, "ref_shim.h")
 CAPI = os.path.join(HERE, "ref_capi.cpp")
-REF_FILES = ["spconv/csrc/sparse/indices.py", "spconv/csrc/sparse/gather.py", "spconv/csrc/sparse/maxpool.py"]
+REF_FILES = ["spconv/csrc/sparse/indices.py", "spconv/csrc/sparse/gather.py", "spconv/csrc/sparse/maxpool.py",
+             "spconv/csrc/sparse/pointops.py"]
 
 
 def reference_available() -> bool:
@@ -95,6 +98,8 @@ class _Any:
         self._name = name
 
     def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
         return _Any(f"{self._name}.{item}")
 
     def __call__(self, *a, **k):
@@ -117,6 +122,7 @@ class _PccmClass:
     def add_member(self, name, ctype, *a, **k): self._members.append((name, ctype))
     def add_static_const(self, *a, **k): pass
     def add_enum_class(self, *a, **k): pass
+    def add_pybind_member(self, *a, **k): pass
 
     @property
     def class_name(self):
@@ -137,8 +143,8 @@ def _install_stubs():
         sys.modules[name] = m
         return m
 
-    def unpack(name, rng):          # cumm.gemm.codeops.unpack: "x[0], x[1], ..."
-        return ", ".join(f"{name}[{i}]" for i in rng)
+    def unpack(name, rng, left="[", right="]"):   # cumm.gemm.codeops.unpack: "x[0], x[1], ..."
+        return ", ".join(f"{name}{left}{i}{right}" for i in rng)
 
     def unpack_str(name, rng):      # "h_0, h_1, ..."
         return ", ".join(f"{name}_{i}" for i in rng)
@@ -150,10 +156,12 @@ def _install_stubs():
             code.raw("}")
 
     pccm = mod("pccm", FunctionCode=FunctionCode, code=FunctionCode, ParameterizedClass=_PccmClass,
-               Class=_PccmClass, literal=lambda v: repr(v))
+               Class=_PccmClass, literal=lambda v: repr(v),
+               boolean=lambda v: "true" if v else "false")
     pccm.cuda = _Any("pccm.cuda")
     pccm.pybind = _Any("pccm.pybind")
-    dtypes = mod("cumm.dtypes", int32=_DType("int32_t"), int64=_DType("int64_t"))
+    pccm.pybind.PybindClassMixin = type("PybindClassMixin", (), {})          # used as a base class
+    dtypes = mod("cumm.dtypes", int32=_DType("int32_t"), int64=_DType("int64_t"), float32=_DType("float"))
     mod("cumm", dtypes=dtypes)
     mod("cumm.gemm")
     mod("cumm.gemm.core")
@@ -234,6 +242,19 @@ def generate() -> str:
     out.append(_emit_fn("gather", g.gather(), True))
     out.append(_emit_fn("scatter_add", g.scatter_add(), True))
     out.append("};\n")
+    pts = _load(os.path.join(REF_ROOT, REF_FILES[3]), "_ref_pointops")
+    for ndim in (2, 3):
+        out.append(f"namespace ref_p2v{ndim} {{\n")
+        common = pts.Point2VoxelCommon(dtypes.float32, ndim, True)
+        out.append("struct Point2VoxelCommon {\n")
+        out.append(_emit_fn("calc_meta_data", common.calc_meta_data(), True))
+        out.append("};\n")
+        cpu = pts.Point2VoxelCPU(dtypes.float32, ndim, True)
+        out.append("struct Point2VoxelCPU {\n")
+        out.append(_emit_fn("point_to_voxel_static", cpu.point_to_voxel_static_template(False), True))
+        out.append(_emit_fn("point_to_voxel_empty_mean_static", cpu.point_to_voxel_static_template(True), True))
+        out.append("};\n")
+        out.append(f"}}  // namespace ref_p2v{ndim}\n")
     mp = mpl.IndiceMaxPoolCPU()
     out.append("struct IndiceMaxPoolCPU {\n")
     out.append(_emit_fn("global_pool_rearrange", mp.global_pool_rearrange(), True))

@@ -529,3 +529,84 @@ def global_pool_rearrange(coords: np.ndarray, batch_size: int):
                 out[b, counts[b]] = i
                 counts[b] += 1
     return out, counts
+
+
+# ---------------------------------------------------------------------------- point -> voxel
+def point2voxel_meta(vsize_xyz, coors_range_xyz):
+    """``Point2VoxelCommon::calc_meta_data`` (``pointops.py:42-88``) through the reference's own code
+    when ``oracle/_ref`` is built: zyx-ordered ``(vsize[3], grid[3], stride[3], range[6])``."""
+    r = ref_lib()
+    if r is None:
+        raise RuntimeError("oracle/_ref is not built")
+    vs = np.zeros(3, np.float32); grid = np.zeros(3, np.int32); stride = np.zeros(3, np.int64); rng = np.zeros(6, np.float32)
+    a = np.ascontiguousarray(vsize_xyz, dtype=np.float32); b = np.ascontiguousarray(coors_range_xyz, dtype=np.float32)
+    r.ref_point2voxel_meta_3d(_ptr(a), _ptr(b), _ptr(vs), _ptr(grid), _ptr(stride), _ptr(rng))
+    return vs, grid, stride, rng
+
+
+def point2voxel_ref(points: np.ndarray, vsize_xyz, coors_range_xyz, max_voxels: int, max_points: int,
+                    empty_mean: bool = False):
+    """The reference's CPU voxel generator (``Point2VoxelCPU::point_to_voxel_static``,
+    ``pointops.py:589-695``) run through ``oracle/_ref``.  NOTE its ``empty_mean`` variant never resets
+    the running mean between voxels (``mean_value.clear()`` on a sized-by-constructor vector,
+    :676-680), so only ``empty_mean=False`` is a usable oracle."""
+    r = ref_lib()
+    if r is None:
+        raise RuntimeError("oracle/_ref is not built")
+    r.ref_point2voxel_3d.restype = ctypes.c_int
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n, nf = pts.shape
+    vs, grid, _, rng = point2voxel_meta(vsize_xyz, coors_range_xyz)
+    voxels = np.zeros((max_voxels, max_points, nf), np.float32)
+    indices = np.zeros((max_voxels, 3), np.int32)
+    num = np.zeros((max_voxels,), np.int32)
+    dense = np.full(tuple(int(g) for g in grid), -1, np.int32)
+    ids = np.zeros((n,), np.int64)
+    m = r.ref_point2voxel_3d(_ptr(pts), n, nf, _ptr(voxels), _ptr(indices), _ptr(num), _ptr(dense), _ptr(ids), _ptr(vs),
+                             _ptr(grid), _ptr(rng), int(max_voxels), int(max_points), int(bool(empty_mean)), 1)
+    return voxels[:m].copy(), indices[:m].copy(), num[:m].copy(), ids
+
+
+def point2voxel(points: np.ndarray, vsize_xyz, coors_range_xyz, max_voxels: int, max_points: int,
+                empty_mean: bool = False):
+    """numpy restatement of the same algorithm (first-touch voxel ids, first ``max_points`` points per
+    voxel in input order); ``empty_mean`` uses the proper per-voxel mean (what the reference's GPU
+    kernel ``voxel_empty_fill_mean`` computes, ``pointops.py:252-281``)."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n, nf = pts.shape
+    nd = len(vsize_xyz)
+    vs = np.array([vsize_xyz[nd - 1 - j] for j in range(nd)], np.float32)
+    lo = np.array([coors_range_xyz[nd - 1 - j] for j in range(nd)], np.float32)
+    hi = np.array([coors_range_xyz[2 * nd - 1 - j] for j in range(nd)], np.float32)
+    grid = np.round((hi - lo) / vs).astype(np.int64)
+    c = np.floor((pts[:, [nd - 1 - j for j in range(nd)]] - lo) / vs).astype(np.int64)
+    ok = ((c >= 0) & (c < grid)).all(axis=1)
+    key = np.zeros(n, np.int64)
+    for j in range(nd):
+        key = key * grid[j] + c[:, j]
+    ids = np.full(n, -1, np.int64)
+    voxels = np.zeros((max_voxels, max_points, nf), np.float32)
+    indices = np.zeros((max_voxels, nd), np.int32)
+    num = np.zeros(max_voxels, np.int32)
+    seen = {}
+    m = 0
+    for i in range(n):
+        if not ok[i]:
+            continue
+        v = seen.get(key[i])
+        if v is None:
+            if m >= max_voxels:          # voxel dropped: its points get no id (pointops.py:643-647)
+                continue
+            v = m
+            m += 1
+            seen[key[i]] = v
+            indices[v] = c[i]
+        ids[i] = v
+        if num[v] < max_points:
+            voxels[v, num[v]] = pts[i]
+            num[v] += 1
+    if empty_mean:
+        for v in range(m):
+            if 0 < num[v] < max_points:
+                voxels[v, num[v]:] = voxels[v, :num[v]].mean(axis=0, dtype=np.float32)
+    return voxels[:m], indices[:m], num[:m], ids

@@ -86,6 +86,34 @@ void ref_global_pool_rearrange(int32_t *out_indices, const int32_t *coords, int3
                                             t_i32(counts, {batch}));
 }
 
+// Point2VoxelCPU::point_to_voxel_static / _empty_mean_static (pointops.py:589-695), 3-D zyx.
+// densehash: int32 [grid_size...] filled with -1 by the caller (spconv/pytorch/utils.py:56-60).
+// vsize / grid / range are in INTERNAL (zyx) order as calc_meta_data returns them.  Returns the voxel count.
+int ref_point2voxel_3d(const float *points, int n, int nf, float *voxels, int32_t *indices, int32_t *num_per_voxel,
+                       int32_t *densehash, int64_t *pc_voxel_id, const float *vsize, const int *grid,
+                       const float *range, int max_voxels, int max_points, int empty_mean, int clear_voxels) {
+    std::array<float, 3> vs{vsize[0], vsize[1], vsize[2]};
+    std::array<int, 3> gs{grid[0], grid[1], grid[2]}, gstride{grid[1] * grid[2], grid[2], 1};
+    std::array<float, 6> cr{range[0], range[1], range[2], range[3], range[4], range[5]};
+    tv::Tensor pts = t_f32(points, {n, nf}), vox = t_f32(voxels, {max_voxels, max_points, nf});
+    tv::Tensor ind = t_i32(indices, {max_voxels, 3}), num = t_i32(num_per_voxel, {max_voxels});
+    tv::Tensor dh = t_i32(densehash, {grid[0], grid[1], grid[2]});
+    tv::Tensor ids(pc_voxel_id, {n}, tv::int64);
+    auto res = empty_mean
+        ? ref_p2v3::Point2VoxelCPU::point_to_voxel_empty_mean_static(pts, vox, ind, num, dh, ids, vs, gs, gstride, cr, clear_voxels != 0)
+        : ref_p2v3::Point2VoxelCPU::point_to_voxel_static(pts, vox, ind, num, dh, ids, vs, gs, gstride, cr, clear_voxels != 0);
+    return (int)std::get<0>(res).dim(0);
+}
+
+// Point2VoxelCommon::calc_meta_data (pointops.py:42-88): xyz inputs -> internal-order vsize[3], grid[3], range[6]
+void ref_point2voxel_meta_3d(const float *vsize_xyz, const float *range_xyz, float *vsize, int *grid, int64_t *stride,
+                             float *range) {
+    auto r = ref_p2v3::Point2VoxelCommon::calc_meta_data({vsize_xyz[0], vsize_xyz[1], vsize_xyz[2]},
+                                                         {range_xyz[0], range_xyz[1], range_xyz[2], range_xyz[3], range_xyz[4], range_xyz[5]});
+    for (int i = 0; i < 3; ++i) { vsize[i] = std::get<0>(r)[i]; grid[i] = std::get<1>(r)[i]; stride[i] = std::get<2>(r)[i]; }
+    for (int i = 0; i < 6; ++i) range[i] = std::get<3>(r)[i];
+}
+
 int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

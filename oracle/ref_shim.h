@@ -18,8 +18,11 @@
  *                              GatherCPU, gather.py:25-26; -fopenmp would split it into ranges)
  */
 #pragma once
+#include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <tuple>
 #include <limits>
 #include <sstream>
 #include <stdexcept>
@@ -32,6 +35,7 @@
 
 #define TV_HOST_DEVICE_INLINE inline
 #define TV_DECLTYPE(x) std::decay_t<decltype(x)>
+#define TV_IF_CONSTEXPR constexpr
 #define TV_ASSERT_RT_ERR(cond, ...)                                                       \
     do {                                                                                  \
         if (!(cond)) {                                                                    \
@@ -69,6 +73,18 @@ enum DType { float32 = 0, float64 = 1, int32 = 2, int64 = 3 };
 struct half_t {};
 struct bfloat16_t {};
 
+// row-major N-d accessor: view(i, j, k)
+template <typename T, int N> struct TensorView {
+    T *p;
+    int64_t shape[N];
+    template <class... I> T &operator()(I... idx) const {
+        const int64_t ii[sizeof...(I)] = {(int64_t)idx...};
+        int64_t off = 0;
+        for (int a = 0; a < (int)sizeof...(I); ++a) off = off * shape[a] + ii[a];
+        return p[off];
+    }
+};
+
 struct Tensor {
     void *ptr = nullptr;
     std::vector<int64_t> shape;
@@ -82,6 +98,22 @@ struct Tensor {
         return s;
     }
     template <typename T> T *data_ptr() const { return reinterpret_cast<T *>(const_cast<void *>(ptr)); }
+    template <typename T, int N> TensorView<T, N> tview() const {
+        TensorView<T, N> v;
+        v.p = data_ptr<T>();
+        for (int a = 0; a < N; ++a) v.shape[a] = shape[a];
+        return v;
+    }
+    size_t itemsize() const { return dt == float64 || dt == int64 ? 8 : 4; }
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+    void zero_() { std::memset(ptr, 0, (size_t)numel() * itemsize()); }
+    Tensor slice_first_axis(int64_t b, int64_t e) const {
+        Tensor r = *this;
+        int64_t inner = shape.empty() ? 1 : numel() / (shape[0] ? shape[0] : 1);
+        r.ptr = (char *)ptr + (size_t)b * inner * itemsize();
+        r.shape[0] = e - b;
+        return r;
+    }
     DType dtype() const { return dt; }
     int device() const { return -1; }
     bool is_cpu() const { return true; }

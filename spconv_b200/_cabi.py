@@ -79,6 +79,13 @@ SIGNATURES = {
     "spx_implicit_gemm_fwd_int8": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p,
                                            c_int, c_void_p, c_void_p, c_void_p, c_float, c_int,
                                            c_float, c_void_p]),
+    "spx_point2voxel_workspace_size": (c_size_t, [c_int64, c_int]),
+    "spx_point2voxel_stage1": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_float), POINTER(c_int),
+                                       POINTER(c_float), c_int64, POINTER(c_int64), POINTER(c_int64), c_void_p,
+                                       c_size_t, c_void_p]),
+    "spx_point2voxel_stage2": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_float), POINTER(c_int),
+                                       POINTER(c_float), c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spx_indice_pool_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int,
                                     c_void_p, c_void_p]),
     "spx_indice_pool_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,

@@ -12,6 +12,7 @@
 //     "Native" pairs come from a stable per-offset scan instead of atomicAggInc.
 #include "common.cuh"
 #include "gemm.cuh"
+#include "hash.cuh"
 #include <cub/cub.cuh>
 
 namespace spx {
@@ -55,101 +56,6 @@ static bool needs_i64(const Geom &g, const int *dims) {
     double v = (double)g.batch;
     for (int a = 0; a < g.ndim; ++a) v *= (double)dims[a];
     return v >= 2147483647.0;
-}
-
-// ------------------------------------------------------------------ hash tables
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
-    return x;
-}
-__device__ __forceinline__ uint32_t mix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-    return (uint32_t)x;
-}
-
-// 32-bit keys: one packed slot, key in the high word so that atomicMin on the slot is a
-// min over the value for equal keys.
-struct Table32 {
-    unsigned long long *slots;
-    uint32_t cap_mask;
-    static constexpr unsigned long long EMPTY = ~0ull;
-    __device__ __forceinline__ void insert_min(int64_t key64, int32_t val) const {
-        uint32_t key = (uint32_t)key64;
-        unsigned long long packed = ((unsigned long long)key << 32) | (uint32_t)val;
-        uint32_t h = mix32(key) & cap_mask;
-        while (true) {
-            unsigned long long prev = atomicCAS(&slots[h], EMPTY, packed);
-            if (prev == EMPTY) return;
-            if ((uint32_t)(prev >> 32) == key) {
-                if ((uint32_t)prev > (uint32_t)val) atomicMin(&slots[h], packed);
-                return;
-            }
-            h = (h + 1) & cap_mask;
-        }
-    }
-    // returns slot index or -1
-    __device__ __forceinline__ int64_t find_slot(int64_t key64, int32_t &val) const {
-        uint32_t key = (uint32_t)key64;
-        uint32_t h = mix32(key) & cap_mask;
-        while (true) {
-            unsigned long long cur = __ldg(&slots[h]);
-            if (cur == EMPTY) return -1;
-            if ((uint32_t)(cur >> 32) == key) { val = (int32_t)(uint32_t)cur; return h; }
-            h = (h + 1) & cap_mask;
-        }
-    }
-    __device__ __forceinline__ bool occupied(uint32_t s, int64_t &key, int32_t &val) const {
-        unsigned long long cur = slots[s];
-        if (cur == EMPTY) return false;
-        key = (int64_t)(uint32_t)(cur >> 32);
-        val = (int32_t)(uint32_t)cur;
-        return true;
-    }
-    __device__ __forceinline__ void set_value(uint32_t s, int32_t val) const {
-        unsigned long long cur = slots[s];
-        slots[s] = (cur & 0xFFFFFFFF00000000ull) | (uint32_t)val;
-    }
-};
-
-// 64-bit keys: split arrays (volume >= 2^31)
-struct Table64 {
-    long long *keys;   // EMPTY = -1
-    int32_t *vals;     // initialised to INT_MAX
-    uint32_t cap_mask;
-    __device__ __forceinline__ void insert_min(int64_t key, int32_t val) const {
-        uint32_t h = mix64((uint64_t)key) & cap_mask;
-        while (true) {
-            long long prev = (long long)atomicCAS((unsigned long long *)&keys[h], (unsigned long long)-1ll,
-                                                  (unsigned long long)key);
-            if (prev == -1ll || prev == key) { atomicMin(&vals[h], val); return; }
-            h = (h + 1) & cap_mask;
-        }
-    }
-    __device__ __forceinline__ int64_t find_slot(int64_t key, int32_t &val) const {
-        uint32_t h = mix64((uint64_t)key) & cap_mask;
-        while (true) {
-            long long cur = keys[h];
-            if (cur == -1ll) return -1;
-            if (cur == key) { val = vals[h]; return h; }
-            h = (h + 1) & cap_mask;
-        }
-    }
-    __device__ __forceinline__ bool occupied(uint32_t s, int64_t &key, int32_t &val) const {
-        long long cur = keys[s];
-        if (cur == -1ll) return false;
-        key = cur; val = vals[s];
-        return true;
-    }
-    __device__ __forceinline__ void set_value(uint32_t s, int32_t val) const { vals[s] = val; }
-};
-
-// load factor <= 0.25: with linear probing the expected miss chain is ~1.4 slots and -- what
-// matters on a GPU -- the MAX chain over the 32 lanes of a warp stays ~2-3 (at 0.5 it was ~6
-// dependent L2 round trips per probe, measured with ncu on the 100 k-voxel cloud)
-static uint32_t table_capacity(int64_t n_items, int factor = 4) {
-    uint64_t cap = 1024;
-    while (cap < (uint64_t)n_items * factor) cap <<= 1;
-    return (uint32_t)cap;
 }
 
 // ------------------------------------------------------------------ coordinate helpers

@@ -150,3 +150,18 @@ def test_pooling_oracle_against_reference_cpu_loop(ref):
     assert np.abs(d_ref - d_np).max() < 1e-6
     oi, cnt = ref.global_pool_rearrange(inds, 2)
     assert cnt.tolist() == [1200, 900] and np.array_equal(oi[1, :900], np.arange(1200, 2100))
+
+
+def test_point2voxel_restatement_against_reference_cpu_generator(ref):
+    """Point2VoxelCPU::point_to_voxel_static (pointops.py:589-695, compiled into oracle/_ref) vs the numpy
+    restatement, incl. the max_num_voxels cap and out-of-range points"""
+    rng = np.random.default_rng(0)
+    pts = rng.uniform([-1, -41, -4, 0], [71, 41, 2, 1], size=(20000, 4)).astype(np.float32)
+    vs, cr = [0.4, 0.4, 0.5], [0, -40, -3, 70.4, 40, 1]
+    for max_voxels, max_points in ((3000, 5), (50000, 2)):
+        a = ref.point2voxel_ref(pts, vs, cr, max_voxels, max_points)
+        b = ref.point2voxel(pts, vs, cr, max_voxels, max_points)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    _, grid, stride, rng6 = ref.point2voxel_meta(vs, cr)
+    assert grid.tolist() == [8, 200, 176] and stride.tolist() == [35200, 176, 1]
