@@ -386,7 +386,9 @@ def int8_conv_forward(features_i8: np.ndarray, filters_i8: np.ndarray, pairs, nu
         n = int(cnt[k])
         if n <= 0:
             continue
-        np.add.at(acc, pairs[1][k, :n], x[pairs[0][k, :n]] @ w[:, k].T)
+        # within one offset every output row occurs at most once (A.3 / A.4), so a fancy-indexed
+        # "+=" is exact here (and ~50x faster than np.add.at at 100 k voxels)
+        acc[pairs[1][k, :n]] += x[pairs[0][k, :n]] @ w[:, k].T
     res = acc.astype(np.float32) * scales.astype(np.float32) + bias.astype(np.float32)
     if output_add is not None:
         res = res + output_add.astype(np.float32) * np.float32(output_add_scale)

@@ -14,3 +14,5 @@ from .pool import (SparseAvgPool1d, SparseAvgPool2d, SparseAvgPool3d, SparseGlob
                    SparseGlobalMaxPool, SparseMaxPool1d, SparseMaxPool2d, SparseMaxPool3d, SparseMaxPool4d)
 from .utils_fuse import (fuse_act, fuse_bn, fuse_bn_act_sequential, fuse_bn_weights)  # noqa: F401
 from . import quantized  # noqa: F401
+from .graph import GraphedStep, graph_capture  # noqa: F401
+from .utils import PointToVoxel, gather_features_by_pc_voxel_id  # noqa: F401

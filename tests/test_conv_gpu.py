@@ -377,3 +377,34 @@ def test_graph_captured_backward_branches_match_eager(cuda_dev):
         torch.cuda.synchronize()
         for got, ref, name in zip(captured, eager, ("out", "din", "dw")):
             assert torch.equal(got, ref), f"{name} differs between graph replay and eager"
+
+
+def test_int8_forward_at_config5_size(oracle, cuda_dev):
+    """BASELINE configs[4] at its stated size: int8 SubMConv3d 3x3x3 C = K = 64 over a ~100 k-voxel
+    KITTI-shaped cloud, per-channel scale + bias + ReLU + clip, exact against the numpy formula
+    (test/test_all_algo.py:272-287) apart from rint ties."""
+    from spconv_b200.core import Activation, ConvAlgo
+    from spconv_b200.pytorch import ops
+    from tests.util import surface_cloud
+    rng = np.random.default_rng(50051)
+    shape = [41, 1600, 1408]
+    inds = surface_cloud(rng, shape, 100_000)
+    C = K = 64
+    x = rng.integers(-127, 128, size=(inds.shape[0], C)).astype(np.int8)
+    w = rng.integers(-127, 128, size=(K, 3, 3, 3, C)).astype(np.int8)
+    out_inds, pairs, num = oracle.get_indice_pairs(inds, 1, shape, [3] * 3, [1] * 3, [1] * 3, [1] * 3, [0] * 3, True)
+    scales = (rng.uniform(0.5, 1.5, size=K) * 2e-4).astype(np.float32)       # per-channel
+    bias = rng.uniform(-5, 5, size=K).astype(np.float32)
+    ref = oracle.int8_conv_forward(x, w, pairs, num, inds.shape[0], True, scales, bias, relu=True, out_int8=True)
+    d_inds = torch.from_numpy(inds).to(cuda_dev)
+    res = ops.get_indice_pairs_implicit_gemm(d_inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3, [1] * 3,
+                                             [1] * 3, [0] * 3, True, False, is_train=False)
+    out, _, _ = ops.implicit_gemm(torch.from_numpy(x).to(cuda_dev), torch.from_numpy(w).to(cuda_dev), res[2], res[4],
+                                  res[6], inds.shape[0], res[8], False, True, bias=torch.from_numpy(bias).to(cuda_dev),
+                                  act_type=Activation.ReLU, scale=torch.from_numpy(scales).to(cuda_dev),
+                                  output_dtype=torch.int8)
+    assert ops.last_kernel_family() == 2, "int8 tcgen05 (kind::i8) path expected"
+    got = out.cpu().numpy()
+    assert 0.05 < (got > 0).mean() < 0.95 and got.max() == 127            # the clip and the ReLU are both exercised
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (diff.max(), (diff > 0).mean())

@@ -255,3 +255,42 @@ def test_quantized_sparse_conv_hookup(subm, oracle, cuda_dev):
     deq = Q.dequantize_tensor(yq).features
     err = (deq - yf.features).abs().max() / yf.features.abs().max()
     assert float(err) < 0.05, float(err)
+
+
+def test_graph_capture_of_a_subm_training_step(cuda_dev):
+    """spconv.graph_capture: a SubM stack's forward + backward replayed as ONE CUDA graph gives the
+    eager result bit for bit; a strided conv inside the captured region is refused with a clear error"""
+    import spconv_b200.pytorch as spconv
+    rng = np.random.default_rng(17)
+    shape = [24, 24, 24]
+    feats, inds = random_cloud(rng, shape, [3000], 32)
+    net = spconv.SparseSequential(spconv.SubMConv3d(32, 32, 3, bias=False, indice_key="k"),
+                                  spconv.SubMConv3d(32, 64, 3, bias=False, indice_key="k")).to(cuda_dev).half()
+    d_inds = torch.from_numpy(inds).to(cuda_dev)
+    params = list(net.parameters())
+
+    def step(f, i):
+        for p in params:
+            p.grad = None
+        y = net(spconv.SparseConvTensor(f, i, shape, 1))
+        loss = y.features.float().square().mean()
+        loss.backward()
+        return loss, [p.grad for p in params]
+
+    f0 = torch.from_numpy(feats).to(cuda_dev).half()
+    loss_e, grads_e = step(f0, d_inds)
+    loss_e, grads_e = loss_e.clone(), [g.clone() for g in grads_e]
+    g = spconv.graph_capture(step, f0, d_inds)
+    f1 = (f0 * 0.5).contiguous()
+    g(f1, d_inds)                                        # different data, same shapes
+    loss_g, grads_g = g(f0, d_inds)
+    assert torch.equal(loss_g, loss_e)
+    for a, b in zip(grads_g, grads_e):
+        assert torch.equal(a, b)
+    down = spconv.SparseConv3d(32, 32, 3, 2, 1, bias=False).to(cuda_dev).half()
+    with pytest.raises(RuntimeError, match="cannot be captured"):
+        spconv.graph_capture(lambda f, i: down(spconv.SparseConvTensor(f, i, shape, 1)).features, f0, d_inds)
+    torch.cuda.synchronize()
+    # the library is usable again after the refused capture
+    y = down(spconv.SparseConvTensor(f0, d_inds, shape, 1))
+    assert torch.isfinite(y.features.float()).all()
