@@ -38,6 +38,26 @@ struct Table32 {
             h = (h + 1) & cap_mask;
         }
     }
+    // insert_min that also reports the slot and whether THIS call created the entry; gives up after
+    // max_probes steps (returns -1): the caller sized the table optimistically and must re-run
+    __device__ __forceinline__ int64_t insert_min_slot(int64_t key64, int32_t val, bool &created, int max_probes) const {
+        uint32_t key = (uint32_t)key64;
+        unsigned long long packed = ((unsigned long long)key << 32) | (uint32_t)val;
+        uint32_t h = mix32(key) & cap_mask;
+        created = false;
+        for (int step = 0; step < max_probes; ++step) {
+            unsigned long long prev = atomicCAS(&slots[h], EMPTY, packed);
+            if (prev == EMPTY) { created = true; return h; }
+            if ((uint32_t)(prev >> 32) == key) {
+                if ((uint32_t)prev > (uint32_t)val) atomicMin(&slots[h], packed);
+                return h;
+            }
+            h = (h + 1) & cap_mask;
+        }
+        return -1;
+    }
+    __device__ __forceinline__ int32_t value_at(uint32_t s) const { return (int32_t)(uint32_t)slots[s]; }
+    __device__ __forceinline__ void clear_slot(uint32_t s) const { slots[s] = EMPTY; }
     // returns slot index or -1
     __device__ __forceinline__ int64_t find_slot(int64_t key64, int32_t &val) const {
         uint32_t key = (uint32_t)key64;
@@ -76,6 +96,18 @@ struct Table64 {
             h = (h + 1) & cap_mask;
         }
     }
+    __device__ __forceinline__ int64_t insert_min_slot(int64_t key, int32_t val, bool &created, int max_probes) const {
+        uint32_t h = mix64((uint64_t)key) & cap_mask;
+        created = false;
+        for (int step = 0; step < max_probes; ++step) {
+            long long prev = (long long)atomicCAS((unsigned long long *)&keys[h], (unsigned long long)-1ll,
+                                                  (unsigned long long)key);
+            if (prev == -1ll || prev == key) { created = prev == -1ll; atomicMin(&vals[h], val); return h; }
+            h = (h + 1) & cap_mask;
+        }
+        return -1;
+    }
+    __device__ __forceinline__ int32_t value_at(uint32_t s) const { return vals[s]; }
     __device__ __forceinline__ int64_t find_slot(int64_t key, int32_t &val) const {
         uint32_t h = mix64((uint64_t)key) & cap_mask;
         while (true) {

@@ -16,6 +16,12 @@
 #include <cub/cub.cuh>
 
 namespace spx {
+size_t radix_argsort_workspace_bytes(int64_t n);
+int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+}
+
+namespace spx {
 
 // ------------------------------------------------------------------ geometry
 struct Geom {
@@ -379,6 +385,112 @@ __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restr
     if (mask_bwd) mask_bwd[i] = mword;
 }
 
+
+// ---- append-on-create variants (default path): the thread whose CAS creates a table entry records
+// the slot, so the distinct outputs are known without scanning the (mostly empty) table afterwards.
+// Created slots are staged in shared memory and a block reserves its range of the global list with
+// ONE atomic.  `state`: [0] number of created entries, [1] overflow flag (a probe chain exceeded
+// CONV_MAX_PROBES: the optimistically sized table was too small, the host re-runs with the full size).
+constexpr int CONV_MAX_PROBES = 96;
+constexpr int APPEND_THREADS = 128;
+
+template <typename Table>
+__global__ void __launch_bounds__(APPEND_THREADS)
+conv_insert_k3_append_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N,
+                             uint32_t *__restrict__ slot_list, int *__restrict__ state) {
+    __shared__ uint32_t stage[APPEND_THREADS * 27];
+    __shared__ int cnt_s, base_s;
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) {
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+        if (c.x >= 0 && c.x < g.batch) {
+            const Axis3 az = axis_taps3(c.y, g.padding[0], g.dilation[0], g.stride[0], g.out_dims[0]);
+            const Axis3 ay = axis_taps3(c.z, g.padding[1], g.dilation[1], g.stride[1], g.out_dims[1]);
+            const Axis3 ax = axis_taps3(c.w, g.padding[2], g.dilation[2], g.stride[2], g.out_dims[2]);
+#pragma unroll
+            for (int r0 = 0; r0 < 3; ++r0) {
+                if (az.o[r0] < 0) continue;
+                const int64_t kz = (int64_t)c.x * g.out_dims[0] + az.o[r0];
+#pragma unroll
+                for (int r1 = 0; r1 < 3; ++r1) {
+                    if (ay.o[r1] < 0) continue;
+                    const int64_t kzy = kz * g.out_dims[1] + ay.o[r1];
+#pragma unroll
+                    for (int r2 = 0; r2 < 3; ++r2) {
+                        if (ax.o[r2] < 0) continue;
+                        const int k = (r0 * 3 + r1) * 3 + r2;
+                        bool created;
+                        const int64_t slot = table.insert_min_slot(kzy * g.out_dims[2] + ax.o[r2],
+                                                                   (int32_t)((int64_t)k * N + i), created, CONV_MAX_PROBES);
+                        if (slot < 0) state[1] = 1;
+                        else if (created) stage[atomicAdd(&cnt_s, 1)] = (uint32_t)slot;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = cnt_s;
+    if (threadIdx.x == 0) base_s = cnt ? atomicAdd(state, cnt) : 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += APPEND_THREADS) slot_list[base_s + j] = stage[j];
+}
+
+// grid (ceil(N/T), kv): one (input, offset) per thread -> at most one creation per thread
+template <typename Table, bool FAST3>
+__global__ void __launch_bounds__(APPEND_THREADS)
+conv_insert_append_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N,
+                          uint32_t *__restrict__ slot_list, int *__restrict__ state) {
+    __shared__ int warp_cnt[APPEND_THREADS / 32];
+    __shared__ int base_s;
+    __shared__ Taps3 taps;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (FAST3 && threadIdx.x == 0) taps = block_taps3(g, k);
+    __syncthreads();
+    bool created = false;
+    int64_t slot = 0;
+    if (i < N) {
+        int64_t key = 0;
+        bool valid;
+        if constexpr (FAST3) {
+            const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+            valid = conv3_out_key(g, c, taps, key);
+        } else {
+            int c[SPX_MAX_NDIM + 1], o[SPX_MAX_NDIM + 1], r[SPX_MAX_NDIM];
+            load_coord(indices, i, g.ndim, c);
+            offset_taps(k, g.ksize, g.ndim, r);
+            valid = conv_out_coord(g, c, r, o);
+            if (valid) key = linear_key(o, g.out_dims, g.ndim);
+        }
+        if (valid) {
+            slot = table.insert_min_slot(key, (int32_t)((int64_t)k * N + i), created, CONV_MAX_PROBES);
+            if (slot < 0) { state[1] = 1; created = false; }
+        }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, created);
+    if (lane == 0) warp_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < APPEND_THREADS / 32; ++w) { const int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+        base_s = tot ? atomicAdd(state, tot) : 0;
+    }
+    __syncthreads();
+    if (created) slot_list[base_s + warp_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (uint32_t)slot;
+}
+
+// first-touch payload of every created slot (final only after ALL inserts: atomicMin keeps lowering it)
+template <typename Table>
+__global__ void conv_fetch_payload_kernel(Table table, const uint32_t *__restrict__ slot_list, int64_t M,
+                                          uint32_t *__restrict__ payload) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < M) payload[j] = (uint32_t)table.value_at(slot_list[j]);
+}
+
 // compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next).
 // The table is sized for the worst-case output count, so most of it is empty: every thread scans
 // COLLECT_ITEMS slots and a block reserves its output range with ONE atomic (a single global
@@ -429,11 +541,12 @@ conv_collect_kernel(Table table, uint32_t capacity, uint32_t *__restrict__ paylo
 
 // rank r (first-touch order) -> write r into its slot, decode the key into out_inds[r]
 template <typename Table>
-__global__ void conv_assign_kernel(Table table, Geom g, const uint32_t *__restrict__ sorted_slot, int64_t M,
-                                   int32_t *__restrict__ out_inds) {
+__global__ void conv_assign_kernel(Table table, Geom g, const uint32_t *__restrict__ sorted_slot,
+                                   const int32_t *__restrict__ order, int64_t M, int32_t *__restrict__ out_inds) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= M) return;
-    uint32_t s = sorted_slot[r];
+    // order != NULL: sorted_slot is the UNSORTED slot list and order the argsort of its payloads
+    uint32_t s = order ? sorted_slot[order[r]] : sorted_slot[r];
     int64_t key; int32_t val;
     table.occupied(s, key, val);
     table.set_value(s, (int32_t)r);
@@ -825,8 +938,9 @@ extern "C" size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_
         max_out = spx_conv_max_out(g, num_in);   // the bound is recomputed by both stages
         RbLayout L = rb_layout(gg, max_out, gg.out_dims, 2);
         total += align_up(L.table_bytes, 256) + align_up(L.table_vals_bytes, 256);
-        total += 4 * align_up((size_t)max_out * 4, 256);          // payload, slot (in + out)
+        total += 5 * align_up((size_t)max_out * 4, 256);          // payload, slot (in + out), order
         total += align_up(sort_pairs_temp_bytes(max_out), 256);
+        total += align_up(radix_argsort_workspace_bytes(max_out), 256);
         total += 256;                                             // counter
     }
     return total + 1024;
@@ -886,14 +1000,30 @@ extern "C" int spx_subm_rulebook(const spx_conv_geometry *g, const int32_t *indi
     return 0;
 }
 
+
 namespace {
 struct ConvWs {
     void *tbl; int32_t *tvals;
     uint32_t *payload, *slot, *payload_sorted, *slot_sorted;
     void *sort_tmp; size_t sort_tmp_bytes;
+    int32_t *order;                    // argsort of the payloads (default path)
+    void *radix_ws; size_t radix_ws_bytes;
     int *counter;
     RbLayout L;
 };
+// which table capacity stage 1 ended up with (the optimistic size, or the full one after an overflow);
+// stage 2 is called right after stage 1 on the same thread with the same workspace
+struct ConvStage1Record { const void *ws; uint32_t capacity; bool legacy; };
+thread_local ConvStage1Record g_stage1 = {nullptr, 0, false};
+
+// Optimistic table size: the bound on the outputs (spx_conv_max_out, e.g. 8 N for 3^3 stride 2) is what
+// isolated points would produce; LiDAR-like clouds yield ~0.5 N.  A table for a quarter of the bound
+// (load <= 0.5 if M <= bound / 4) is cleared and probed 4x cheaper; a probe chain longer than
+// CONV_MAX_PROBES flags an overflow and stage 1 re-runs with the full size.
+uint32_t optimistic_capacity(int64_t max_out, uint32_t full_capacity) {
+    uint32_t cap = table_capacity((max_out + 3) / 4, 2);
+    return cap < full_capacity ? cap : full_capacity;
+}
 int carve_conv_ws(const spx_conv_geometry *g, const Geom &gg, int64_t N, void *workspace, size_t bytes, ConvWs &w) {
     int64_t max_out = spx_conv_max_out(g, N);
     w.L = rb_layout(gg, max_out, gg.out_dims, 2);
@@ -906,6 +1036,9 @@ int carve_conv_ws(const spx_conv_geometry *g, const Geom &gg, int64_t N, void *w
     w.slot_sorted = ws.take<uint32_t>(max_out);
     w.sort_tmp_bytes = sort_pairs_temp_bytes(max_out);
     w.sort_tmp = ws.take<char>(w.sort_tmp_bytes);
+    w.order = ws.take<int32_t>(max_out);
+    w.radix_ws_bytes = radix_argsort_workspace_bytes(max_out);
+    w.radix_ws = ws.take<char>(w.radix_ws_bytes);
     w.counter = ws.take<int>(64);
     SPX_REQUIRE(ws.ok(), "rulebook workspace too small: need %zu, have %zu", ws.off, bytes);
     return 0;
@@ -931,6 +1064,52 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
     const bool fast3 = gg.ndim == 3 && !gg.transposed;
     const bool k3 = fast3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
+    const bool legacy = (runtime_cfg().debug & 128) != 0;
+    g_stage1 = {workspace, w.L.capacity, legacy};
+    if (!legacy) {
+        // ---- default path: optimistic table, append-on-create, own radix sort of the first-touch payloads
+        const int64_t max_out = spx_conv_max_out(g, N);
+        int host_state[2] = {0, 0};
+        uint32_t capacity = optimistic_capacity(max_out, w.L.capacity);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, (size_t)capacity * 8, stream));
+            SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(int), stream));
+            if (!w.L.i64) {
+                Table32 t{(unsigned long long *)w.tbl, capacity - 1};
+                if (k3) conv_insert_k3_append_kernel<<<(unsigned)div_up64(N, APPEND_THREADS), APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+                else if (fast3) conv_insert_append_kernel<Table32, true><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+                else conv_insert_append_kernel<Table32, false><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+            } else {
+                SPX_CHECK_CUDA(cudaMemsetAsync(w.tvals, 0x7F, (size_t)capacity * 4, stream));
+                Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
+                if (k3) conv_insert_k3_append_kernel<<<(unsigned)div_up64(N, APPEND_THREADS), APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+                else if (fast3) conv_insert_append_kernel<Table64, true><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+                else conv_insert_append_kernel<Table64, false><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
+            }
+            SPX_CHECK_LAUNCH("conv_insert_append_kernel");
+            SPX_CHECK_CUDA(cudaMemcpyAsync(host_state, w.counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            SPX_CHECK_CUDA(cudaStreamSynchronize(stream));
+            if (!host_state[1]) break;
+            SPX_REQUIRE(capacity < w.L.capacity, "conv rulebook: hash table overflow at full capacity (%u slots)", capacity);
+            capacity = w.L.capacity;                     // rare: far more outputs than the optimistic guess
+        }
+        g_stage1.capacity = capacity;
+        const int m_host = host_state[0];
+        *num_out_host = m_host;
+        if (m_host == 0) return 0;
+        const unsigned mblk = (unsigned)div_up64(m_host, 256);
+        if (!w.L.i64) {
+            Table32 t{(unsigned long long *)w.tbl, capacity - 1};
+            conv_fetch_payload_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.payload);
+        } else {
+            Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
+            conv_fetch_payload_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.payload);
+        }
+        SPX_CHECK_LAUNCH("conv_fetch_payload_kernel");
+        int key_bits = 1;
+        while (key_bits < 32 && ((int64_t)1 << key_bits) < (int64_t)gg.kv * N) ++key_bits;
+        return radix_argsort(w.payload, w.order, m_host, key_bits, w.radix_ws, w.radix_ws_bytes, stream);
+    }
     SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
     SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
     unsigned cblk = (unsigned)div_up64(w.L.capacity, COLLECT_THREADS * COLLECT_ITEMS);
@@ -984,17 +1163,21 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
     const bool fast3 = gg.ndim == 3 && !gg.transposed;
     const bool k3 = fast3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
     SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));
+    SPX_REQUIRE(g_stage1.ws == workspace && g_stage1.capacity != 0,
+                "conv_rulebook_stage2 must follow conv_rulebook_stage1 on the same thread with the same workspace");
+    const bool legacy = g_stage1.legacy;
+    const uint32_t capacity = g_stage1.capacity;
     if (!w.L.i64) {
-        Table32 t{(unsigned long long *)w.tbl, w.L.capacity - 1};
-        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
+        Table32 t{(unsigned long long *)w.tbl, capacity - 1};
+        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, legacy ? w.slot_sorted : w.slot, legacy ? nullptr : w.order, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
         if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
         else if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     } else {
-        Table64 t{(long long *)w.tbl, w.tvals, w.L.capacity - 1};
-        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, M, out_inds);
+        Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
+        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, legacy ? w.slot_sorted : w.slot, legacy ? nullptr : w.order, M, out_inds);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
         if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
         else if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
@@ -1067,11 +1250,6 @@ extern "C" int spx_pairs_to_table(const int32_t *pairs, const int32_t *indice_pa
     return 0;
 }
 
-namespace spx {
-size_t radix_argsort_workspace_bytes(int64_t n);
-int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
-                  cudaStream_t stream);
-}
 
 extern "C" size_t spx_mask_argsort_workspace_size(int64_t N, int words) {
     if (N <= 0) return 256;

@@ -34,3 +34,25 @@ for n in (100_000, 800_000):
         else:
             print("   argsort identical to legacy:", bool(torch.equal(keep, srt)))
 _cabi.check(_cabi.load().spx_debug_configure(-1, 0, 0, None, 0), "cfg")
+
+# ---- regular conv rulebook (configs[3] shape): legacy (full table + scan-collect + CUB) vs default
+shape4 = [41, 1440, 1440]
+rng = np.random.default_rng(50051)
+inds4 = torch.from_numpy(surface_cloud(rng, shape4, 300_000)).to(dev)
+keep = None
+for dbg, name in ((128 | 64, "legacy"), (0, "default")):
+    _cabi.check(_cabi.load().spx_debug_configure(-1, 0, dbg, None, 0), "cfg")
+    acc = {}
+    for rep in range(6):
+        timer = CUDAKernelTimer(True)
+        flush.zero_(); torch.cuda._sleep(800_000)
+        res = ops.get_indice_pairs_implicit_gemm(inds4, 1, shape4, ConvAlgo.MaskImplicitGemm, [3] * 3, [2] * 3, [1] * 3,
+                                                 [1] * 3, [0] * 3, False, False, is_train=True, timer=timer)
+        for k, v in timer.get_all_pair_time().items():
+            acc.setdefault(k, []).append(v)
+    print(f"conv k3s2 N=300000 M={res[0].shape[0]} {name:8s}", {k: round(float(np.median(v)) * 1e3, 1) for k, v in acc.items()}, "us")
+    if keep is None:
+        keep = [t.clone() for t in (res[0], res[2], res[3], res[6][0], res[7][0])]
+    else:
+        print("   identical to legacy:", all(bool(torch.equal(a, b)) for a, b in zip(keep, (res[0], res[2], res[3], res[6][0], res[7][0]))))
+_cabi.check(_cabi.load().spx_debug_configure(-1, 0, 0, None, 0), "cfg")
