@@ -16,13 +16,15 @@
 // The first pass reads the masks with an implicit iota payload, the last pass writes the sorted
 // masks back in place (thrust semantics) and the argsort.
 //
-// Default path ("onesweep"): ONE kernel per pass.  The digit totals of every pass do not depend on
+// Experimental path ("onesweep", debug bit 64 of spx_debug_configure): ONE kernel per pass.  The digit totals of every pass do not depend on
 // the key order, so a single histogram kernel counts all passes up front; a pass kernel then needs
 // only the number of equal digits in the tiles BEFORE its own, which it gets by decoupled
 // look-back over per-tile status words {count | flag} (tile ids are drawn from an atomic ticket, so
 // every predecessor is already running and publishes its aggregate before it waits on anyone).
-// 1 + passes launches instead of 1 + 2 * passes; the legacy two-kernel passes stay selectable with
-// debug bit 64 (spx_debug_configure) for A/B runs.
+// 1 + passes launches instead of 1 + 2 * passes -- but MEASURED SLOWER on B200 (100 k keys: 51.7 vs
+// 45.5 us; 800 k keys: 109 vs 93 us; profiles/r02_ab_rulebook.log): the per-digit look-back is a chain
+// of dependent L2 round trips that costs more than the scan kernel + launch gap it replaces.  Kept
+// for A/B runs only; results are bit-identical.
 #include "common.cuh"
 
 namespace spx {
@@ -353,7 +355,7 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
     const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
     const uint32_t *kin = mask;
     const int32_t *vin = nullptr;
-    if (!(runtime_cfg().debug & 64)) {
+    if (runtime_cfg().debug & 64) {
         // ---- onesweep: memset(scratch) + histogram of all passes + one kernel per pass
         const size_t head_ints = (size_t)OS_MAX_PASSES * RS_BINS + 64;        // hist[4][512] + tickets
         int *head = ws.take<int>(head_ints);

@@ -204,7 +204,7 @@ def test_mask_split_implicit_gemm_is_a_real_split(subm, oracle, cuda_dev):
     for m in (a, b):
         xf = torch.from_numpy(feats).to(cuda_dev).half().requires_grad_(True)
         y = m(spconv.SparseConvTensor(xf, d_inds, shape, 1))
-        y.features.float().square().mean().backward()
+        (y.features.float().square().sum() * 1e-2).backward()       # keeps fp16 gradients out of the subnormals
         outs.append((y.features.detach().float(), xf.grad.float(), m.weight.grad.float(), m.bias.grad.float()))
     for u, v in zip(*outs):
         assert rel_l2(v.cpu().numpy(), u.cpu().numpy()) < 5e-3

@@ -16,7 +16,7 @@ for n in (100_000, 800_000):
     rng = np.random.default_rng(50051)
     inds = torch.from_numpy(surface_cloud(rng, shape, n if n <= 100_000 else 100_000, batch=max(1, n // 100_000))).to(dev)
     bs = max(1, n // 100_000)
-    for dbg, name in ((64, "legacy"), (0, "onesweep")):
+    for dbg, name in ((0, "two-kernel"), (64, "onesweep")):
         _cabi.check(_cabi.load().spx_debug_configure(-1, 0, dbg, None, 0), "cfg")
         acc = {}
         ref = None
@@ -29,7 +29,7 @@ for n in (100_000, 800_000):
                 acc.setdefault(k, []).append(v)
         print(f"N={inds.shape[0]:7d} {name:9s}", {k: round(float(np.median(v)) * 1e3, 1) for k, v in acc.items()}, "us")
         srt = res[6][0].clone()
-        if dbg == 64:
+        if dbg == 0:
             keep = srt
         else:
             print("   argsort identical to legacy:", bool(torch.equal(keep, srt)))
@@ -40,7 +40,7 @@ shape4 = [41, 1440, 1440]
 rng = np.random.default_rng(50051)
 inds4 = torch.from_numpy(surface_cloud(rng, shape4, 300_000)).to(dev)
 keep = None
-for dbg, name in ((128 | 64, "legacy"), (0, "default")):
+for dbg, name in ((128, "legacy"), (0, "default")):
     _cabi.check(_cabi.load().spx_debug_configure(-1, 0, dbg, None, 0), "cfg")
     acc = {}
     for rep in range(6):
