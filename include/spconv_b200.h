@@ -126,6 +126,29 @@ int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_t *indices,
                              size_t workspace_bytes, spx_stream_t stream);
 
 /*
+ * Fused host entry points: one call = the launches of spx_subm_rulebook + spx_mask_argsort +
+ * spx_build_tile_table (resp. spx_conv_rulebook_stage2 + both argsorts + both tile tables), all
+ * scratch carved from ONE workspace.  They exist because an eager Python caller pays ~10 us of
+ * interpreter / ctypes / allocator time per separate call; results are identical.
+ * `mask` is left sorted; tile_table / tile_mask (spx_tile_table_elems, tiles * words) may be NULL to
+ * skip the tile table.  argsort_bwd / table_bwd may be NULL (inference: no backward direction).
+ * spx_conv_rulebook_stage2_all continues a spx_conv_rulebook_stage1 that was given a workspace of
+ * spx_conv_rulebook_all_workspace_size bytes.
+ */
+size_t spx_subm_rulebook_all_workspace_size(const spx_conv_geometry *g, int64_t N);
+int spx_subm_rulebook_all(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                          int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask, int32_t *argsort,
+                          int do_sort, int32_t *tile_table, uint32_t *tile_mask, void *workspace,
+                          size_t workspace_bytes, spx_stream_t stream);
+size_t spx_conv_rulebook_all_workspace_size(const spx_conv_geometry *g, int64_t N);
+int spx_conv_rulebook_stage2_all(const spx_conv_geometry *g, const int32_t *indices, int64_t N,
+                                 int64_t M, int32_t *out_inds, int32_t *pair_fwd, int32_t *pair_bwd,
+                                 uint32_t *mask_fwd, uint32_t *mask_bwd, int32_t *argsort_fwd,
+                                 int32_t *argsort_bwd, int do_sort, int32_t *table_fwd,
+                                 uint32_t *tmask_fwd, int32_t *table_bwd, uint32_t *tmask_bwd,
+                                 void *workspace, size_t workspace_bytes, spx_stream_t stream);
+
+/*
  * Compact "Native" rulebook  pairs [2, kv, N] (-1 padded) + indice_pair_num [kv]  in the
  * reference CPU order (ascending input index per offset), derived from pair_bwd [kv, N] by a
  * stable scan.  For SubM only offsets < kv/2 are counted and their mirrors written, the centre

@@ -56,6 +56,13 @@ SIGNATURES = {
     "spx_conv_rulebook_stage2": (c_int, [POINTER(ConvGeometry), c_void_p, c_int64, c_int64,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_size_t, c_void_p]),
+    "spx_subm_rulebook_all_workspace_size": (c_size_t, [POINTER(ConvGeometry), c_int64]),
+    "spx_subm_rulebook_all": (c_int, [POINTER(ConvGeometry), c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spx_conv_rulebook_all_workspace_size": (c_size_t, [POINTER(ConvGeometry), c_int64]),
+    "spx_conv_rulebook_stage2_all": (c_int, [POINTER(ConvGeometry), c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spx_native_pairs": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     "spx_native_pairs_workspace_size": (c_size_t, [c_int64, c_int]),

@@ -1340,3 +1340,81 @@ extern "C" int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, in
     SPX_CHECK_LAUNCH("tile_order_kernel");
     return 0;
 }
+
+// ====================================================================== fused host entry points
+// One C-ABI call per rulebook (the eager Python path was paying ~10 us of interpreter + ctypes +
+// allocator time for every separate call, workspace query and scratch tensor).  Pure orchestration:
+// the launches are exactly those of the separate entry points, scratch regions are carved from ONE
+// caller-provided workspace.
+
+static size_t subm_row_table_bytes(const spx_conv_geometry *g, int64_t N) {
+    return spx_subm_row_table_supported(g) ? align_up((size_t)N * 32 * sizeof(int32_t), 256) : 0;
+}
+
+extern "C" size_t spx_subm_rulebook_all_workspace_size(const spx_conv_geometry *g, int64_t N) {
+    if (!g || g->ndim < 1 || g->ndim > SPX_MAX_NDIM) return 0;
+    int kv = 1;
+    for (int a = 0; a < g->ndim; ++a) kv *= g->ksize[a];
+    const size_t a = spx_rulebook_workspace_size(g, N, 0, 1);
+    const size_t b = spx_mask_argsort_workspace_size(N, (kv + 31) / 32);
+    return align_up(a > b ? a : b, 256) + subm_row_table_bytes(g, N) + 256;
+}
+
+extern "C" int spx_subm_rulebook_all(const spx_conv_geometry *g, const int32_t *indices, int64_t N, int32_t *pair_fwd,
+                                     int32_t *pair_bwd, uint32_t *mask, int32_t *argsort, int do_sort,
+                                     int32_t *tile_table, uint32_t *tile_mask, void *workspace, size_t workspace_bytes,
+                                     spx_stream_t stream) {
+    if (validate_geom(g)) return 2;
+    if (N == 0) return 0;
+    SPX_REQUIRE(mask && argsort && workspace, "subm_rulebook_all: NULL pointer argument");
+    SPX_REQUIRE(workspace_bytes >= spx_subm_rulebook_all_workspace_size(g, N), "subm_rulebook_all: workspace too small");
+    int kv = 1;
+    for (int a = 0; a < g->ndim; ++a) kv *= g->ksize[a];
+    const int words = (kv + 31) / 32;
+    const size_t rb = spx_rulebook_workspace_size(g, N, 0, 1), as = spx_mask_argsort_workspace_size(N, words);
+    const size_t shared = align_up(rb > as ? rb : as, 256);          // rulebook and sort scratch are used one after the other
+    int32_t *row_table = subm_row_table_bytes(g, N) ? (int32_t *)((char *)workspace + shared) : nullptr;
+    if (int rc = spx_subm_rulebook(g, indices, N, pair_fwd, pair_bwd, mask, row_table, workspace, rb, stream)) return rc;
+    if (int rc = spx_mask_argsort(mask, argsort, N, words, kv, do_sort, workspace, as, stream)) return rc;
+    if (tile_table)
+        return spx_build_tile_table(pair_fwd, N, kv, argsort, mask, N, row_table, tile_table, tile_mask, stream);
+    return 0;
+}
+
+extern "C" size_t spx_conv_rulebook_all_workspace_size(const spx_conv_geometry *g, int64_t N) {
+    if (!g || g->ndim < 1 || g->ndim > SPX_MAX_NDIM) return 0;
+    int kv = 1;
+    for (int a = 0; a < g->ndim; ++a) kv *= g->ksize[a];
+    const int64_t max_rows = spx_conv_max_out(g, N) > N ? spx_conv_max_out(g, N) : N;
+    return align_up(spx_rulebook_workspace_size(g, N, 0, 0), 256) +
+           align_up(spx_mask_argsort_workspace_size(max_rows, (kv + 31) / 32), 256) + 256;
+}
+
+// stage 2 + both mask argsorts + both tile tables (argsort_bwd / table_bwd may be NULL: inference)
+extern "C" int spx_conv_rulebook_stage2_all(const spx_conv_geometry *g, const int32_t *indices, int64_t N, int64_t M,
+                                            int32_t *out_inds, int32_t *pair_fwd, int32_t *pair_bwd, uint32_t *mask_fwd,
+                                            uint32_t *mask_bwd, int32_t *argsort_fwd, int32_t *argsort_bwd, int do_sort,
+                                            int32_t *table_fwd, uint32_t *tmask_fwd, int32_t *table_bwd,
+                                            uint32_t *tmask_bwd, void *workspace, size_t workspace_bytes,
+                                            spx_stream_t stream) {
+    if (validate_geom(g)) return 2;
+    if (N == 0 || M == 0) return 0;
+    SPX_REQUIRE(mask_fwd && mask_bwd && argsort_fwd && workspace, "conv_rulebook_stage2_all: NULL pointer argument");
+    SPX_REQUIRE(workspace_bytes >= spx_conv_rulebook_all_workspace_size(g, N), "conv_rulebook_stage2_all: workspace too small");
+    int kv = 1;
+    for (int a = 0; a < g->ndim; ++a) kv *= g->ksize[a];
+    const int words = (kv + 31) / 32;
+    const size_t rb = spx_rulebook_workspace_size(g, N, 0, 0);
+    void *sort_ws = (char *)workspace + align_up(rb, 256);
+    const size_t sort_bytes = workspace_bytes - align_up(rb, 256);
+    if (int rc = spx_conv_rulebook_stage2(g, indices, N, M, out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd, workspace, rb, stream)) return rc;
+    if (int rc = spx_mask_argsort(mask_fwd, argsort_fwd, M, words, kv, do_sort, sort_ws, sort_bytes, stream)) return rc;
+    if (table_fwd)
+        if (int rc = spx_build_tile_table(pair_fwd, M, kv, argsort_fwd, mask_fwd, M, nullptr, table_fwd, tmask_fwd, stream)) return rc;
+    if (argsort_bwd) {
+        if (int rc = spx_mask_argsort(mask_bwd, argsort_bwd, N, words, kv, do_sort, sort_ws, sort_bytes, stream)) return rc;
+        if (table_bwd)
+            if (int rc = spx_build_tile_table(pair_bwd, N, kv, argsort_bwd, mask_bwd, N, nullptr, table_bwd, tmask_bwd, stream)) return rc;
+    }
+    return 0;
+}

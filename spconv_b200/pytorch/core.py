@@ -20,6 +20,17 @@ from ..core import ConvAlgo
 TensorOrSparse = Union["SparseConvTensor", torch.Tensor]
 
 
+class _NullRegion:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_REGION = _NullRegion()
+
+
 class CUDAKernelTimer:
     """Named CUDA-event regions, active only when ``enable`` (reference ``spconv/tools.py:23-78``)."""
 
@@ -28,21 +39,26 @@ class CUDAKernelTimer:
         self._scope: List[str] = []
         self._events: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
 
-    @contextmanager
     def namespace(self, name: str):
-        if self.enable:
-            self._scope.append(name)
+        if not self.enable:
+            return _NULL_REGION
+        return self._namespace(name)
+
+    @contextmanager
+    def _namespace(self, name: str):
+        self._scope.append(name)
         try:
             yield self
         finally:
-            if self.enable:
-                self._scope.pop()
+            self._scope.pop()
 
-    @contextmanager
     def record(self, name: str, stream: int = 0):
         if not self.enable:
-            yield self
-            return
+            return _NULL_REGION          # no generator / context objects on the hot path
+        return self._record(name)
+
+    @contextmanager
+    def _record(self, name: str):
         begin, finish = (torch.cuda.Event(enable_timing=True) for _ in range(2))
         begin.record()
         try:
@@ -56,11 +72,15 @@ class CUDAKernelTimer:
         a layer land under the same prefix as its forward regions)."""
         return tuple(self._scope)
 
-    @contextmanager
     def scoped(self, scope: Sequence[str]):
+        if not self.enable:
+            return _NULL_REGION
+        return self._scoped(scope)
+
+    @contextmanager
+    def _scoped(self, scope: Sequence[str]):
         saved = self._scope
-        if self.enable:
-            self._scope = list(scope)
+        self._scope = list(scope)
         try:
             yield self
         finally:

@@ -43,8 +43,21 @@ def _lib():
     return _cabi.load()
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device.  (``torch.cuda.current_stream()``
+    costs ~4 us of Python per call -- 76 calls per encoder step were a fifth of the eager host time.)"""
+    return _raw_stream(_cur_device())
+
+
+def _prod(xs) -> int:
+    r = 1
+    for x in xs:
+        r *= int(x)
+    return r
 
 
 _SIDE_STREAMS: dict = {}
@@ -120,13 +133,36 @@ def _out_shape(spatial_shape, ksize, stride, padding, dilation, out_padding, sub
     return shape
 
 
+_GEO_CACHE: dict = {}
+
+
 def _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding, dilation,
               transpose):
     ndim = indices.shape[1] - 1
     if not (1 <= ndim <= _cabi.SPX_MAX_NDIM):
         raise RuntimeError(f"unsupported ndim {ndim}")
-    return _cabi.make_geometry(ndim, batch_size, spatial_shape, out_shape, ksize, stride, padding,
-                               dilation, transpose)
+    key = (ndim, int(batch_size), tuple(spatial_shape), tuple(out_shape), tuple(ksize), tuple(stride),
+           tuple(padding), tuple(dilation), bool(transpose))
+    geo = _GEO_CACHE.get(key)
+    if geo is None:                      # the struct is immutable once built: layers re-use it every step
+        if len(_GEO_CACHE) > 4096:
+            _GEO_CACHE.clear()
+        geo = _GEO_CACHE[key] = _cabi.make_geometry(ndim, batch_size, spatial_shape, out_shape, ksize, stride,
+                                                    padding, dilation, transpose)
+    return geo
+
+
+_ZERO_COUNTS: dict = {}
+
+
+def _zero_counts(kv: int, device) -> torch.Tensor:
+    """``indice_num_per_loc`` of the implicit-GEMM rulebooks: not consumed by the GEMM, kept
+    for the shape of the reference's 9-tuple; one read-only zeros tensor per (kv, device)."""
+    key = (kv, device)
+    t = _ZERO_COUNTS.get(key)
+    if t is None:
+        t = _ZERO_COUNTS[key] = torch.zeros((kv,), dtype=torch.int32, device=device)
+    return t
 
 
 def _conv_rulebook(geo, indices, n_in, kv, words, want_masks, alloc):
@@ -154,6 +190,42 @@ def _conv_rulebook(geo, indices, n_in, kv, words, want_masks, alloc):
                                              ws.data_ptr(), ws.numel(), _stream()),
                 "conv_rulebook_stage2")
     return out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd
+
+
+def _conv_rulebook_all(geo, indices, n_in, kv, words, is_train, do_sort, alloc, indice_num_per_loc, masks):
+    """Regular-conv implicit-GEMM rulebook in two native calls (stage 1 with its host read-back of the
+    output count, then stage 2 + both mask sorts + both tile tables)."""
+    lib = _lib()
+    dev = indices.device
+    ws = _bytes(lib.spx_conv_rulebook_all_workspace_size(ctypes.byref(geo), n_in), dev, alloc)
+    m_host = ctypes.c_int64(0)
+    _cabi.check(lib.spx_conv_rulebook_stage1(ctypes.byref(geo), _ptr(indices), n_in, ctypes.byref(m_host),
+                                             ws.data_ptr(), ws.numel(), _stream()), "conv_rulebook_stage1")
+    m = int(m_host.value)
+    if m == 0:
+        raise ValueError(_VANISHED)
+    ndim = indices.shape[1] - 1
+    out_inds = torch.empty((m, ndim + 1), dtype=torch.int32, device=dev)
+    pair_fwd = torch.empty((kv, m), dtype=torch.int32, device=dev)
+    pair_bwd = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+    mask_fwd = torch.empty((1, m, words), dtype=torch.int32, device=dev)
+    mask_bwd = torch.empty((1, n_in, words), dtype=torch.int32, device=dev)
+    sort_fwd = torch.empty((1, m), dtype=torch.int32, device=dev)
+    sort_bwd = torch.empty((1, n_in), dtype=torch.int32, device=dev) if is_train else None
+    t_fwd, tm_fwd = _alloc_tile_tables(m, kv, dev)
+    t_bwd, tm_bwd = _alloc_tile_tables(n_in, kv, dev) if is_train else (None, None)
+    _cabi.check(lib.spx_conv_rulebook_stage2_all(
+        ctypes.byref(geo), _ptr(indices), n_in, m, out_inds.data_ptr(), pair_fwd.data_ptr(), pair_bwd.data_ptr(),
+        mask_fwd.data_ptr(), mask_bwd.data_ptr(), sort_fwd.data_ptr(), _ptr(sort_bwd), int(bool(do_sort)),
+        _ptr(t_fwd), _ptr(tm_fwd), _ptr(t_bwd), _ptr(tm_bwd), ws.data_ptr(), ws.numel(), _stream()),
+        "conv_rulebook_stage2_all")
+    sf = sort_fwd[0]
+    sf._spx_tile_cache = (_tile_key(pair_fwd, sf, m), t_fwd, tm_fwd)
+    if not is_train:
+        return (out_inds, indice_num_per_loc, pair_fwd, pair_bwd, [mask_fwd[0]], [], [sf], [], masks)
+    sb = sort_bwd[0]
+    sb._spx_tile_cache = (_tile_key(pair_bwd, sb, n_in), t_bwd, tm_bwd)
+    return (out_inds, indice_num_per_loc, pair_fwd, pair_bwd, [mask_fwd[0]], [mask_bwd[0]], [sf], [sb], masks)
 
 
 def _argsort_masks(mask: torch.Tensor, kv: int, do_sort: bool, alloc) -> torch.Tensor:
@@ -197,7 +269,7 @@ def get_indice_pairs(indices: torch.Tensor, batch_size: int, spatial_shape: List
     dev = indices.device
     indices = indices.contiguous()
     n_in = indices.shape[0]
-    kv = int(np.prod(ksize))
+    kv = _prod(ksize)
     out_shape = _out_shape(spatial_shape, ksize, stride, padding, dilation, out_padding, subm,
                            transpose)
     geo = _geometry(indices, batch_size, spatial_shape, out_shape, ksize, stride, padding,
@@ -244,7 +316,7 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
     dev = indices.device
     indices = indices.contiguous()
     n_in = indices.shape[0]
-    kv = int(np.prod(ksize))
+    kv = _prod(ksize)
     words = (kv + 31) // 32
     if kv > 128:
         raise NotImplementedError("masked implicit gemm supports kernel volume <= 128")
@@ -261,13 +333,27 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
     else:
         masks = [np.array([0xffffffff], dtype=np.uint32)]
     # per-offset pair counts are not consumed by the GEMM; kept for API shape
-    indice_num_per_loc = torch.zeros((kv,), dtype=torch.int32, device=dev)
+    indice_num_per_loc = _zero_counts(kv, dev)
     if subm:
         for k in ksize:
             if k % 2 != 1:
                 raise RuntimeError("subm only support odd ksize")
         pair = torch.empty((2 if is_train else 1, kv, n_in), dtype=torch.int32, device=dev)
         pair_mask = torch.empty((1, n_in, words), dtype=torch.int32, device=dev)
+        if not timer.enable and not is_split and n_in:
+            # one native call: hash + probe + mask sort + tile table (the separate calls below are kept
+            # for profiling regions and the mask-split algo)
+            mask_argsort = torch.empty((1, n_in), dtype=torch.int32, device=dev)
+            table, tile_mask = _alloc_tile_tables(n_in, kv, dev)
+            ws = _bytes(lib.spx_subm_rulebook_all_workspace_size(ctypes.byref(geo), n_in), dev, alloc)
+            _cabi.check(lib.spx_subm_rulebook_all(ctypes.byref(geo), _ptr(indices), n_in, pair[0].data_ptr(),
+                                                  pair[1].data_ptr() if is_train else None, _ptr(pair_mask),
+                                                  _ptr(mask_argsort), int(bool(do_sort)), _ptr(table), _ptr(tile_mask),
+                                                  ws.data_ptr(), ws.numel(), _stream()), "subm_rulebook_all")
+            pair_fwd, argsort_view = pair[0], mask_argsort[0]
+            argsort_view._spx_tile_cache = (_tile_key(pair_fwd, argsort_view, n_in), table, tile_mask)
+            return (indices, indice_num_per_loc, pair_fwd, pair[1] if is_train else torch.Tensor(),
+                    [pair_mask[0]], [], [argsort_view], [], masks)
         # row-major by-product of the probe kernel; consumed (and dropped) by the first tile-table build
         rows = None
         if n_in and lib.spx_subm_row_table_supported(ctypes.byref(geo)):
@@ -291,6 +377,8 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
             argsort_view._spx_row_table = (pair[0].data_ptr(), rows)
         return (indices, indice_num_per_loc, pair[0], pair_bwd, [pair_mask[0]], [],
                 [argsort_view], [], masks)
+    if not timer.enable and not is_split and n_in:
+        return _conv_rulebook_all(geo, indices, n_in, kv, words, is_train, do_sort, alloc, indice_num_per_loc, masks)
     with timer.record("gen_conv_inds", _stream()):
         out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd = _conv_rulebook(
             geo, indices, n_in, kv, words, True, alloc)
@@ -315,23 +403,32 @@ def _f32_mode() -> int:
     return _cabi.SPX_F32_TF32 if SPCONV_ALLOW_TF32 else _cabi.SPX_F32_EXACT
 
 
+def _tile_key(pair: torch.Tensor, argsort: Optional[torch.Tensor], rows: int):
+    return (pair.data_ptr(), tuple(pair.shape), pair._version,
+            None if argsort is None else (argsort.data_ptr(), argsort._version), int(rows))
+
+
+def _alloc_tile_tables(rows: int, kv: int, device):
+    tiles = max((int(rows) + MASK_WIDTH - 1) // MASK_WIDTH, 1)
+    # layout of include/spconv_b200.h: blocks + schedule records + scheduler scratch (== spx_tile_table_elems)
+    table = torch.empty((tiles * (kv + 1) * 128 + tiles * 8 + 64,), dtype=torch.int32, device=device)
+    tile_mask = torch.empty((tiles, (kv + 31) // 32), dtype=torch.int32, device=device)
+    return table, tile_mask
+
+
 def _tile_tables(pair: torch.Tensor, mask: Optional[torch.Tensor], argsort: Optional[torch.Tensor],
                  rows: int, kv: int, owner: Optional[torch.Tensor] = None):
     """Tile-blocked gather table + per-tile OR masks for (pair, mask, argsort)
     (``spx_build_tile_table``).  Built once per rulebook and cached on ``owner`` (the argsort
     tensor that lives in the cached ``ImplicitGemmIndiceData``), so forward, input-gradient and
     weight-gradient of every layer sharing the ``indice_key`` reuse it."""
-    key = (pair.data_ptr(), tuple(pair.shape), pair._version,
-           None if argsort is None else (argsort.data_ptr(), argsort._version), int(rows))
+    key = _tile_key(pair, argsort, rows)
     if owner is not None:
         hit = getattr(owner, "_spx_tile_cache", None)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
     lib = _lib()
-    words = (kv + 31) // 32
-    tiles = max((int(rows) + MASK_WIDTH - 1) // MASK_WIDTH, 1)
-    table = torch.empty((lib.spx_tile_table_elems(int(rows), kv),), dtype=torch.int32, device=pair.device)
-    tile_mask = torch.empty((tiles, words), dtype=torch.int32, device=pair.device)
+    table, tile_mask = _alloc_tile_tables(rows, kv, pair.device)
     row_table = None
     hint = getattr(owner, "_spx_row_table", None) if owner is not None else None
     if hint is not None and hint[0] == pair.data_ptr() and hint[1].shape[0] == int(rows):
@@ -368,7 +465,7 @@ def _check_filter(features, filters):
         raise RuntimeError(f"features ({features.dtype}) and filters ({filters.dtype}) must have the same dtype")
     if features.dtype not in _DTYPE_CODE:
         raise RuntimeError(f"unsupported dtype {features.dtype}")
-    kv = int(np.prod(filters.shape[1:-1]))
+    kv = _prod(filters.shape[1:-1])
     return kv, int(filters.shape[-1]), int(filters.shape[0])
 
 
@@ -541,7 +638,7 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
                                                     _ptr(dfilters), ws.data_ptr(), ws.numel(),
                                                     _stream()), "implicit_gemm_wgrad")
 
-    if timer.enable or not (n_in and n_out) or not torch.cuda.is_current_stream_capturing():
+    if timer.enable or not (n_in and n_out) or not torch._C._cuda_isCurrentStreamCapturing():
         # eager launches are host-bound (and an eager fork/join per call measured slower, not
         # faster); profiling regions stay one kernel each
         run_dgrad()

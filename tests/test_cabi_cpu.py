@@ -73,3 +73,14 @@ def test_argument_validation_reports_errors(lib):
     assert "kernel volume" in _cabi.last_error()
     with pytest.raises(RuntimeError, match="kernel volume"):
         _cabi.check(2, "x")
+
+
+def test_tile_table_elems_formula_matches_the_library():
+    """ops._tile_tables sizes the table buffer without a native call; the formula must stay equal to
+    spx_tile_table_elems (layout documented in include/spconv_b200.h)"""
+    from spconv_b200 import _cabi
+    lib = _cabi.load()
+    for rows in (1, 127, 128, 129, 100_000, 1_234_567):
+        for kv in (1, 8, 27, 81, 128):
+            tiles = max((rows + 127) // 128, 1)
+            assert lib.spx_tile_table_elems(rows, kv) == tiles * (kv + 1) * 128 + tiles * 8 + 64
