@@ -5,11 +5,15 @@ TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 echo "== session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40) > $O/${TAG}_tests.log
-tail -4 $O/${TAG}_tests.log
-(timeout 100 python tools/host_profile.py cfg2 50 > $O/${TAG}_hostprof_cfg2.log 2>&1); head -2 $O/${TAG}_hostprof_cfg2.log
-(timeout 100 python tools/host_profile.py encoder 30 > $O/${TAG}_hostprof_enc.log 2>&1); head -2 $O/${TAG}_hostprof_enc.log
-(timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 400 $O/${TAG}_bench.err; head -c 600 $O/${TAG}_bench.json; echo
-(timeout 120 python tools/ab_rulebook.py > $O/${TAG}_ab_rulebook.log 2>&1); cat $O/${TAG}_ab_rulebook.log | tail -20
-(timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_ncu_launches.csv python bench.py --graph 0 --extras 0 --steps 2 --warmup 1 > $O/${TAG}_ncu_bench.log 2>&1); tail -2 $O/${TAG}_ncu_bench.log | cut -c1-200
+(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60) > $O/${TAG}_tests.log
+tail -6 $O/${TAG}_tests.log | cut -c1-300
+(timeout 100 python tools/host_profile.py cfg2 50 > $O/${TAG}_hostprof_cfg2.log 2>&1); head -1 $O/${TAG}_hostprof_cfg2.log
+(timeout 100 python tools/host_profile.py encoder 30 > $O/${TAG}_hostprof_enc.log 2>&1); head -1 $O/${TAG}_hostprof_enc.log
+(timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
+(timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err); head -c 200 $O/${TAG}_bench_reference.json; echo
+(timeout 120 python tools/ab_rulebook.py > $O/${TAG}_ab_rulebook.log 2>&1); tail -12 $O/${TAG}_ab_rulebook.log | cut -c1-250
+(timeout 120 python tools/triage/tools_trace_wgrad.py > $O/${TAG}_trace_wgrad.txt 2>&1); tail -4 $O/${TAG}_trace_wgrad.txt | cut -c1-250
+(timeout 120 python tools/triage/tools_cta_spans.py > $O/${TAG}_cta_spans.txt 2>&1); head -8 $O/${TAG}_cta_spans.txt | cut -c1-200
+(timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches.csv python bench.py --graph 0 --extras 0 --steps 2 --warmup 1 > $O/${TAG}_ncu_bench.log 2>&1); tail -1 $O/${TAG}_ncu_bench.log | cut -c1-120
+(timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_|wgrad_reduce' -c 8 -o $O/${TAG}_full python bench.py --graph 0 --extras 0 --steps 1 --warmup 1 > $O/${TAG}_ncu_full.log 2>&1); ls -la $O/${TAG}_full.ncu-rep 2>/dev/null
 echo "== done $(date -u +%H:%M:%S)"
