@@ -764,7 +764,9 @@ def run_ours(args):
     head = measure(make_workload(args.workload, ctx), ctx, args.steps, args.warmup, True)
     others = {}
     if extras:
-        for name in EXTRA_WORKLOADS:
+        # at N > 1 only the encoder (BASELINE configs[2] is the multi-GPU config) rides along: every
+        # extra workload is another chance for one rank to fail inside a collective
+        for name in (EXTRA_WORKLOADS if world == 1 else EXTRA_WORKLOADS[:1]):
             if name == args.workload:
                 continue
             ctx.torch.cuda.empty_cache()
