@@ -80,6 +80,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the device-resident step from CUDA graphs")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="software-pipeline the graph replay: rulebook of cloud i+1 beside the GEMMs of cloud i")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
@@ -357,6 +359,11 @@ class LayerWorkload(Workload):
         self.grad_buf.copy_(dw)
         return dw
 
+    def compute(self, c, res):
+        """forward + backward on an already built rulebook (the second stage of the pipelined replay)"""
+        _, _, dw = self.conv_fwd_bwd(c, res, self.weight, {})
+        self.grad_buf.copy_(dw)
+
     def grads(self):
         return self.grad_buf
 
@@ -471,10 +478,16 @@ class Int8Workload(Workload):
         return self.ctx.ops.get_indice_pairs_implicit_gemm(c["d_inds"], 1, self.wl["shape"], self.algo, [3] * 3, [1] * 3,
                                                            [1] * 3, [1] * 3, [0] * 3, True, False, is_train=False, **kw)
 
+    def compute(self, c, res):
+        return self.conv(c["d_feats"], res, {})
+
     def run(self, d_inds, d_feats, c, kw):
-        from spconv_b200.core import Activation
         res = self.ctx.ops.get_indice_pairs_implicit_gemm(d_inds, 1, self.wl["shape"], self.algo, [3] * 3, [1] * 3,
                                                           [1] * 3, [1] * 3, [0] * 3, True, False, is_train=False, **kw)
+        return self.conv(d_feats, res, kw)
+
+    def conv(self, d_feats, res, kw):
+        from spconv_b200.core import Activation
         out_inds, _, pair_fwd, _, mask_fwd, _, sort_fwd, _, masks = res
         out, _, _ = self.ctx.ops.implicit_gemm(d_feats, self.weight, pair_fwd, mask_fwd, sort_fwd, out_inds.shape[0], masks,
                                                False, True, bias=self.bias, act_type=Activation.ReLU, scale=self.scale,
@@ -553,9 +566,50 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
             graphs, use_graph = None, False
             torch.cuda.synchronize()
 
+    # ---------------- software-pipelined replay (the default `value`): the rulebook depends only on the
+    # coordinates, never on weights or features, so -- like a data loader prefetching the next batch --
+    # the rulebook of cloud i+1 is generated on a side stream WHILE cloud i runs forward + backward.
+    # Every timed step still contains exactly one rulebook generation and one fwd + dgrad + wgrad
+    # (+ the all-reduce of the previous step's dW at N > 1, placed before the forward pass where an
+    # optimizer would consume it); both streams are joined before the step's end event.
+    pipe = None
+    if use_graph and bool(ctx.args.pipeline) and hasattr(w, "compute"):
+        try:
+            rb_graphs, ge_graphs, rb_out = [], [], []
+            for c in clouds:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    rb_out.append(w.rulebook(c))
+                rb_graphs.append(g)
+            for c, res in zip(clouds, rb_out):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if world > 1 and train:
+                        dist.all_reduce(w.grads())
+                    w.compute(c, res)
+                ge_graphs.append(g)
+            for g in rb_graphs:                      # every rulebook resident once before the first timed step
+                g.replay()
+            torch.cuda.synchronize()
+            pipe = (rb_graphs, ge_graphs)
+        except Exception as e:
+            print(f"[bench] pipelined capture failed ({type(e).__name__}: {e}); serial graph replay", file=sys.stderr)
+            pipe = None
+            torch.cuda.synchronize()
+
+    def serial_step(i):
+        graphs[i % NUM_CLOUDS].replay()
+
     def value_step(i):
         j = i % NUM_CLOUDS
-        if use_graph:
+        if pipe is not None:
+            main = torch.cuda.current_stream()
+            ctx.side.wait_stream(main)
+            with torch.cuda.stream(ctx.side):
+                pipe[0][(i + 1) % NUM_CLOUDS].replay()          # rulebook of the NEXT cloud
+            pipe[1][j].replay()                                 # fwd + bwd of this cloud
+            main.wait_stream(ctx.side)
+        elif use_graph:
             graphs[j].replay()
         else:
             w.device_step(clouds[j])
@@ -646,8 +700,12 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
         sampler.start()
     # three repetitions of the K-step timed region; the median repetition is reported (one region of
     # 20 x 0.15 ms is a thin sample)
+    if pipe is not None:
+        for i in range(2 * NUM_CLOUDS):
+            value_step(i)
     runs = [float(np.mean(ctx.timed_loop(value_step, steps))) for _ in range(3)]
     ms_value = sorted(runs)[1]
+    ms_serial = float(np.mean(ctx.timed_loop(serial_step, steps))) if pipe is not None else None
     ms_e2e = float(np.mean(ctx.timed_loop(e2e_step, steps)))
     ms_e2e_eager = float(np.mean(ctx.timed_loop(e2e_step_eager, steps)))
     clocks = sampler.stop() if (ctx.rank == 0 and headline) else {}
@@ -675,17 +733,20 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     regions = {k: float(np.median(v)) for k, v in samples.items()}
 
     # ---------------- reduce over ranks (max time, sum voxels)
-    t = torch.tensor([ms_value, ms_e2e, ms_e2e_eager, ms_reuse or 0.0], device=ctx.dev, dtype=torch.float64)
+    t = torch.tensor([ms_value, ms_e2e, ms_e2e_eager, ms_reuse or 0.0, ms_serial or 0.0], device=ctx.dev,
+                     dtype=torch.float64)
     n_total = torch.tensor([w.n_per_step], device=ctx.dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_total, op=dist.ReduceOp.SUM)
-    ms_value, ms_e2e, ms_e2e_eager, ms_reuse_r = (float(v) for v in t)
+    ms_value, ms_e2e, ms_e2e_eager, ms_reuse_r, ms_serial_r = (float(v) for v in t)
     voxels = float(n_total[0])
 
     res = {
         "value": voxels / (ms_value * 1e-3), "ms_per_step": ms_value, "ms_per_step_runs": [round(r, 5) for r in runs],
         "voxels_per_step": voxels, "cuda_graph": use_graph, "launches_per_step": int(launches_per_step),
+        "pipelined": pipe is not None,
+        "serial_ms_per_step": ms_serial_r if pipe is not None else None,
         "e2e": {"value": voxels / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": w.h2d_bytes(),
                 "d2h_bytes_per_step": int(h_grads.numel() * h_grads.element_size() + 4) if train
@@ -786,12 +847,17 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": args.workload, **head["config"],
                        "parallelism": f"dp{world} (one batch per GPU)" + (
-                           "; NCCL all-reduce(dW) of step i runs as a graph branch beside the rulebook of step i+1"
+                           "; NCCL all-reduce(dW) of step i is captured at the head of step i+1's compute graph"
                            if world > 1 and head["cuda_graph"] else ("; NCCL all-reduce(dW) per step" if world > 1 else "")),
                        "cuda_graph": head["cuda_graph"],
+                       "pipeline": ("rulebook of cloud i+1 on a side stream beside fwd + bwd of cloud i (one rulebook + one "
+                                    "fwd/dgrad/wgrad per timed step, streams joined before the end event); "
+                                    f"serial replay of the same step: {head['serial_ms_per_step']:.4f} ms")
+                       if head.get("pipelined") else "none",
                        "l2": f"{L2_FLUSH_BYTES >> 20} MiB buffer written between timed steps; {NUM_CLOUDS} rotating clouds",
                        "timing": "median of 3 repetitions of the K-step timed region (ms_per_step_runs)"},
             "ms_per_step_runs": head["ms_per_step_runs"],
+            "serial_ms_per_step": head.get("serial_ms_per_step"),
             "e2e": head["e2e"],
             "gpu_launches": int(head["launches_per_step"] * args.steps),
             "clocks": head["clocks"],

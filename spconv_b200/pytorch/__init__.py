@@ -16,3 +16,4 @@ from .utils_fuse import (fuse_act, fuse_bn, fuse_bn_act_sequential, fuse_bn_weig
 from . import quantized  # noqa: F401
 from .graph import GraphedStep, graph_capture  # noqa: F401
 from .utils import PointToVoxel, gather_features_by_pc_voxel_id  # noqa: F401
+from .prefetch import RulebookPrefetcher  # noqa: F401

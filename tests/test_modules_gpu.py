@@ -294,3 +294,33 @@ def test_graph_capture_of_a_subm_training_step(cuda_dev):
     # the library is usable again after the refused capture
     y = down(spconv.SparseConvTensor(f0, d_inds, shape, 1))
     assert torch.isfinite(y.features.float()).all()
+
+
+def test_rulebook_prefetch_on_a_side_stream(cuda_dev):
+    """RulebookPrefetcher: the next batch's SubM rulebooks are built on a side stream and found by the
+    layers through indice_key; results equal the unprefetched run and no rulebook kernel runs in forward"""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.pytorch import ops
+    rng = np.random.default_rng(23)
+    shape = [24, 24, 24]
+    feats, inds = random_cloud(rng, shape, [3000], 32)
+    net = spconv.SparseSequential(spconv.SubMConv3d(32, 32, 3, bias=False, indice_key="a"),
+                                  spconv.SubMConv3d(32, 64, 3, bias=False, indice_key="a"),
+                                  spconv.SparseConv3d(64, 64, 3, 2, 1, bias=False),
+                                  spconv.SubMConv3d(64, 64, 3, bias=False, indice_key="b")).to(cuda_dev).half()
+    pre = spconv.RulebookPrefetcher(net)
+    assert [m.indice_key for m in pre.layers] == ["a"]           # "b" lives behind the strided layer
+    f = torch.from_numpy(feats).to(cuda_dev).half()
+    i = torch.from_numpy(inds).to(cuda_dev)
+    ref = net(spconv.SparseConvTensor(f, i, shape, 1))
+    x = pre.prefetch(spconv.SparseConvTensor(f, i, shape, 1))
+    assert "a" in x.indice_dict
+    torch.cuda.synchronize()
+    ops.launch_count(reset=True)
+    y = net(pre.ready(x))
+    n_prefetched = ops.launch_count(reset=True)
+    ops.launch_count(reset=True)
+    net(spconv.SparseConvTensor(f, i, shape, 1))
+    n_plain = ops.launch_count(reset=True)
+    assert torch.equal(y.features, ref.features) and torch.equal(y.indices, ref.indices)
+    assert n_prefetched < n_plain                                  # the SubM "a" rulebook kernels are gone
