@@ -201,10 +201,11 @@ class SparseConvTensor:
 
     # ------------------------------------------------------------------ cloning
     def _derive(self, features: torch.Tensor) -> "SparseConvTensor":
-        twin = SparseConvTensor(features, self.indices, self.spatial_shape, self.batch_size,
-                                self.grid, self.voxel_num, self.indice_dict)
-        for name in self._CARRIED:
-            setattr(twin, name, getattr(self, name))
+        """Second handle on the same members with other features.  (Built without re-running the
+        constructor's argument checks: this runs twice per layer on the eager path.)"""
+        twin = object.__new__(SparseConvTensor)
+        twin.__dict__.update(self.__dict__)
+        twin._features = features
         return twin
 
     def replace_feature(self, feature: torch.Tensor) -> "SparseConvTensor":

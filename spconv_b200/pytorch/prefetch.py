@@ -52,7 +52,6 @@ class RulebookPrefetcher:
             self.layers = list(model_or_layers)
         self.stream = stream
         self.training = training
-        self._event: Optional[torch.cuda.Event] = None
 
     def prefetch(self, x: SparseConvTensor) -> SparseConvTensor:
         """Launch the rulebook generation for ``x`` on the side stream and store the results in
@@ -78,16 +77,18 @@ class RulebookPrefetcher:
                     mask_argsort_bwd_splits=sort_bwd, masks=masks, is_subm=True, spatial_shape=x.spatial_shape,
                     out_spatial_shape=x.spatial_shape, algo=algo, ksize=m.kernel_size, stride=m.stride,
                     dilation=m.dilation, padding=m.padding)
-            self._event = torch.cuda.Event()
-            self._event.record(self.stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        x._spx_prefetch_event = ev                   # per tensor: several batches may be in flight
         x.indices.record_stream(self.stream)
         return x
 
     def ready(self, x: SparseConvTensor) -> SparseConvTensor:
         """Make the current stream wait for the prefetch of ``x`` (no host synchronisation)."""
-        if self._event is not None:
-            torch.cuda.current_stream(x.indices.device).wait_event(self._event)
+        ev = getattr(x, "_spx_prefetch_event", None)
+        if ev is not None:
             cur = torch.cuda.current_stream(x.indices.device)
+            cur.wait_event(ev)
             for data in x.indice_dict.values():          # the caching allocator must know the consumer stream
                 for t in (data.pair_fwd, data.pair_bwd, *data.pair_mask_fwd_splits, *data.mask_argsort_fwd_splits):
                     if isinstance(t, torch.Tensor) and t.is_cuda and t.numel():
