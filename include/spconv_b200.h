@@ -214,9 +214,9 @@ typedef struct {
  *   records [tiles][8] int32: {tile, mask words[4], 0, 0, 0}, tiles in order of decreasing
  *             offset count (ties: ascending tile) -- fwd / dgrad CTAs draw tickets from an atomic
  *             counter and take tiles in this order (longest-processing-time-first scheduling);
- *   scratch [64] int32: ticket counter + finished-CTA counter.  Zero after the build and after
- *             every launch (the last CTA resets it); consequently ONE launch at a time may use a
- *             given table (launches on the same stream are fine, concurrent streams are not).
+ *   scratch [64] int32: 32 {ticket counter, finished-CTA counter} pairs.  Zero after the build; every
+ *             launch takes the next pair (round-robin per process) and its last CTA zeroes it again,
+ *             so up to 32 launches may be in flight on one table (other streams, graph branches).
  */
 size_t spx_tile_table_elems(int64_t rows, int kv);
 /*

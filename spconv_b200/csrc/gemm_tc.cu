@@ -27,6 +27,7 @@
 // descriptor b_major = MN), so no transposed copy of the filter is ever made.
 #include "gemm.cuh"
 #include <cuda.h>
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 
@@ -630,8 +631,13 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     {
         const int64_t tiles = div_up64(a.rows, TC_TILE_M);
         p.sched_rec = a.tile_table + tt_blocks_elems(tiles, a.kv);
-        // scheduler scratch lives in the caller's tile-table buffer (include/spconv_b200.h)
-        p.sched_state = const_cast<int *>(reinterpret_cast<const int *>(p.sched_rec + tiles * TT_REC_INTS));
+        // scheduler scratch lives in the caller's tile-table buffer (include/spconv_b200.h): TT_STATE_INTS / 2
+        // {ticket, finished} pairs.  Every launch takes the next pair, so launches that overlap on the
+        // same rulebook (two layers sharing an indice_key on different streams, graph branches) never
+        // draw from one counter; a pair is zero when its launch ends.
+        static std::atomic<unsigned> next_slot{0};
+        const unsigned slot = next_slot.fetch_add(1, std::memory_order_relaxed) % (TT_STATE_INTS / 2);
+        p.sched_state = const_cast<int *>(reinterpret_cast<const int *>(p.sched_rec + tiles * TT_REC_INTS)) + 2 * slot;
     }
     p.kv = a.kv; p.words = (a.kv + 31) / 32; p.reverse = a.reverse;
     p.y = a.y; p.out_dtype = a.dtype; p.epi_mode = 0; p.bias = a.bias; p.act = a.act; p.alpha = a.alpha;
