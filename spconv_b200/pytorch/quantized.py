@@ -76,8 +76,7 @@ class QuantizedSparseConv(SparseConvolution):
         q.register_buffer("weight", w_q.to(mod.weight.device))
         q.register_buffer("weight_scales", w_scales.to(mod.weight.device))
         bias = mod.bias.detach().float() if mod.bias is not None else torch.zeros(mod.out_channels, device=mod.weight.device)
-        if q.bias is not None:
-            del q.bias
+        q._parameters.pop("bias", None)               # Parameter or the registered None placeholder
         q.register_buffer("bias", bias.to(mod.weight.device))        # the reference requires a bias tensor
         q.scale = float(output_scale)
         q.zero_point = 0
