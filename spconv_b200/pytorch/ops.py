@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from .. import _cabi
-from ..constants import SPCONV_ALLOW_TF32, SPCONV_DO_SORT
+from ..constants import SPCONV_ALLOW_TF32, SPCONV_B200_FUSED_RULEBOOK, SPCONV_DO_SORT
 from ..core import Activation, ConvAlgo
 from .core import CUDAKernelTimer, ThrustSortAllocator
 
@@ -340,7 +340,7 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
                 raise RuntimeError("subm only support odd ksize")
         pair = torch.empty((2 if is_train else 1, kv, n_in), dtype=torch.int32, device=dev)
         pair_mask = torch.empty((1, n_in, words), dtype=torch.int32, device=dev)
-        if not timer.enable and not is_split and n_in:
+        if SPCONV_B200_FUSED_RULEBOOK and not timer.enable and not is_split and n_in:
             # one native call: hash + probe + mask sort + tile table (the separate calls below are kept
             # for profiling regions and the mask-split algo)
             mask_argsort = torch.empty((1, n_in), dtype=torch.int32, device=dev)
@@ -377,7 +377,7 @@ def get_indice_pairs_implicit_gemm(indices: torch.Tensor, batch_size: int,
             argsort_view._spx_row_table = (pair[0].data_ptr(), rows)
         return (indices, indice_num_per_loc, pair[0], pair_bwd, [pair_mask[0]], [],
                 [argsort_view], [], masks)
-    if not timer.enable and not is_split and n_in:
+    if SPCONV_B200_FUSED_RULEBOOK and not timer.enable and not is_split and n_in:
         return _conv_rulebook_all(geo, indices, n_in, kv, words, is_train, do_sort, alloc, indice_num_per_loc, masks)
     with timer.record("gen_conv_inds", _stream()):
         out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd = _conv_rulebook(
