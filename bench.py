@@ -81,7 +81,8 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the device-resident step from CUDA graphs")
     ap.add_argument("--pipeline", type=int, default=1,
-                    help="software-pipeline the graph replay: rulebook of cloud i+1 beside the GEMMs of cloud i")
+                    help="software-pipeline the graph replay: 1 = rulebook of cloud i+1 beside the GEMMs of cloud i "
+                         "(streams joined every step), 2 = rulebooks two clouds ahead on two side streams, 0 = serial")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
@@ -236,6 +237,7 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=self.dev)
         self.side = torch.cuda.Stream()
+        self.side2 = torch.cuda.Stream()
 
     def allreduce(self, t):
         if self.world > 1 and t is not None:
@@ -616,9 +618,27 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     def serial_step(i):
         graphs[i % NUM_CLOUDS].replay()
 
+    depth2 = pipe is not None and int(ctx.args.pipeline) >= 2
+    sides = [ctx.side, ctx.side2]
+    ge_done = [torch.cuda.Event() for _ in range(NUM_CLOUDS)]
+
     def value_step(i):
         j = i % NUM_CLOUDS
-        if pipe is not None:
+        if depth2:
+            # rulebooks run TWO clouds ahead, alternating between two side streams: the rulebook of
+            # cloud i was replayed on sides[i % 2] at step i-2; this step waits for it, then queues the
+            # rulebook of cloud i+2 behind it.  No join at the end of the step -- a rulebook that is the
+            # bottleneck shows up as the wait at the head of the step that needs it.
+            main = torch.cuda.current_stream()
+            sd = sides[i % 2]
+            main.wait_stream(sd)
+            jn = (i + 2) % NUM_CLOUDS
+            sd.wait_event(ge_done[jn])                          # the last reader of that cloud's rulebook buffers
+            with torch.cuda.stream(sd):
+                pipe[0][jn].replay()
+            pipe[1][j].replay()
+            ge_done[j].record(main)
+        elif pipe is not None:
             main = torch.cuda.current_stream()
             ctx.side.wait_stream(main)
             with torch.cuda.stream(ctx.side):
@@ -804,7 +824,7 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     res = {
         "value": voxels / (ms_value * 1e-3), "ms_per_step": ms_value, "ms_per_step_runs": [round(r, 5) for r in runs],
         "voxels_per_step": voxels, "cuda_graph": use_graph, "launches_per_step": int(launches_per_step),
-        "pipelined": pipe is not None,
+        "pipelined": (2 if depth2 else 1) if pipe is not None else 0,
         "serial_ms_per_step": ms_serial_r if pipe is not None else None,
         "e2e": {"value": voxels / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": w.h2d_bytes(),
@@ -912,8 +932,11 @@ def run_ours(args):
                            "; NCCL all-reduce(dW) of step i is captured at the head of step i+1's compute graph"
                            if world > 1 and head["cuda_graph"] else ("; NCCL all-reduce(dW) per step" if world > 1 else "")),
                        "cuda_graph": head["cuda_graph"],
-                       "pipeline": ("rulebook of cloud i+1 on a side stream beside fwd + bwd of cloud i (one rulebook + one "
-                                    "fwd/dgrad/wgrad per timed step, streams joined before the end event); "
+                       "pipeline": (("rulebooks two clouds ahead on two alternating side streams (one rulebook + one "
+                                     "fwd/dgrad/wgrad per timed step; a step waits for its own rulebook); "
+                                     if head.get("pipelined") == 2 else
+                                     "rulebook of cloud i+1 on a side stream beside fwd + bwd of cloud i (one rulebook + one "
+                                     "fwd/dgrad/wgrad per timed step, streams joined before the end event); ") +
                                     f"serial replay of the same step: {head['serial_ms_per_step']:.4f} ms")
                        if head.get("pipelined") else "none",
                        "l2": f"{L2_FLUSH_BYTES >> 20} MiB buffer written between timed steps; {NUM_CLOUDS} rotating clouds",
