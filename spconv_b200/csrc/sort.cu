@@ -331,6 +331,163 @@ os_pass_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__
     }
 }
 
+// ------------------------------------------------------------------ cooperative single-kernel path
+// Experimental (debug bit 512 of spx_debug_configure): all passes in ONE cooperative launch, grid
+// barriers instead of kernel boundaries (6 dependent launches of ~4-6 us each are mostly launch /
+// drain latency at 1e5 keys).  Only when every tile's block is co-resident (n <= CS_MAX_BLOCKS tiles);
+// cudaLaunchCooperativeKernel guarantees the co-residency the barrier relies on.
+template <int IT> struct CsCfg { static constexpr int TILE = RS_THREADS * IT; };
+
+__device__ __forceinline__ void cs_grid_barrier(unsigned *bar, unsigned nblocks, unsigned &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned arrived = atomicAdd(&bar[0], 1u);
+        if (arrived == nblocks - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(&bar[1], 1u);                            // release the generation
+        } else {
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile unsigned *>(&bar[1]) == gen) {
+                if (++spins > (1u << 24)) {                    // ~ seconds: a bug must not hang the GPU
+                    printf("spconv_b200: cooperative sort barrier timed out (block %d gen %u)\n", (int)blockIdx.x, gen);
+                    __trap();
+                }
+            }
+        }
+        __threadfence();
+    }
+    ++gen;
+    __syncthreads();
+}
+
+template <int IT>
+__global__ void __launch_bounds__(RS_THREADS)
+cs_sort_kernel(uint32_t *mask, int32_t *argsort, int64_t n, int passes, uint32_t *keys_a, int32_t *vals_a,
+               uint32_t *keys_b, int32_t *vals_b, int *counts, int *totals, unsigned *bar) {
+    constexpr int TILE = RS_THREADS * IT;
+    __shared__ int digit_base[RS_BINS];
+    __shared__ int warp_cnt[RS_WARPS][RS_BINS];
+    __shared__ int scan_tmp[RS_WARPS];
+    __shared__ unsigned gen_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk = blockIdx.x, G = gridDim.x;
+    if (tid == 0) gen_s = *reinterpret_cast<volatile unsigned *>(&bar[1]);
+    __syncthreads();
+    unsigned gen = gen_s;
+    const int64_t tile_base = (int64_t)blk * TILE + warp * (32 * IT);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * RS_BITS;
+        const bool last = pass == passes - 1;
+        const uint32_t *kin = pass == 0 ? mask : ((pass & 1) ? keys_a : keys_b);
+        const int32_t *vin = (pass & 1) ? vals_a : vals_b;
+        uint32_t *kout = last ? mask : ((pass & 1) ? keys_b : keys_a);
+        int32_t *vout = last ? argsort : ((pass & 1) ? vals_b : vals_a);
+        // ---- (1) keys of this tile, per-warp digit counts (= the stable rank bookkeeping), block histogram
+        for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
+        __syncthreads();
+        uint32_t key[IT];
+        int32_t val[IT];
+        int rank[IT];
+#pragma unroll
+        for (int r = 0; r < IT; ++r) {
+            const int64_t i = tile_base + r * 32 + lane;
+            const bool ok = i < n;
+            key[r] = ok ? kin[i] : 0xffffffffu;
+            val[r] = ok ? (pass == 0 ? (int32_t)i : vin[i]) : -1;
+            const int d = ok ? (int)((key[r] >> shift) & (RS_BINS - 1)) : RS_BINS;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            int old = 0;
+            if (ok && lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int d = tid; d < RS_BINS; d += RS_THREADS) {
+            int acc = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) { const int c = warp_cnt[w][d]; warp_cnt[w][d] = acc; acc += c; }
+            counts[(int64_t)d * G + blk] = acc;                 // digit-major
+        }
+        cs_grid_barrier(bar, (unsigned)G, gen);
+        // ---- (2) exclusive prefix over the blocks, one warp per digit; digits dealt to (block, warp)
+        for (int d = blk * RS_WARPS + warp; d < RS_BINS; d += G * RS_WARPS) {
+            int carry = 0;
+            for (int b0 = 0; b0 < G; b0 += 32) {
+                const int b = b0 + lane;
+                const int v = b < G ? counts[(int64_t)d * G + b] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (b < G) counts[(int64_t)d * G + b] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) totals[d] = carry;
+        }
+        cs_grid_barrier(bar, (unsigned)G, gen);
+        // ---- (3) global digit starts (scan of the 512 totals) + this block's share, then scatter
+        int run = 0;
+#pragma unroll
+        for (int q = 0; q < RS_BINS / RS_THREADS; ++q) {
+            const int d = q * RS_THREADS + tid;
+            const int v = *reinterpret_cast<volatile int *>(&totals[d]);
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) scan_tmp[warp] = incl;
+            __syncthreads();
+            int wbase = 0, all = 0;
+            for (int w = 0; w < RS_WARPS; ++w) { if (w < warp) wbase += scan_tmp[w]; all += scan_tmp[w]; }
+            digit_base[d] = run + wbase + incl - v + *reinterpret_cast<volatile int *>(&counts[(int64_t)d * G + blk]);
+            run += all;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < IT; ++r) {
+            const int64_t i = tile_base + r * 32 + lane;
+            if (i < n) {
+                const int d = (int)((key[r] >> shift) & (RS_BINS - 1));
+                const int pos = digit_base[d] + warp_cnt[warp][d] + rank[r];
+                kout[pos] = key[r];
+                vout[pos] = val[r];
+            }
+        }
+        if (!last) cs_grid_barrier(bar, (unsigned)G, gen);
+    }
+}
+
+// blocks of cs_sort_kernel that can be co-resident on the current device (cached per device)
+template <int IT>
+static int cs_max_blocks() {
+    static int cached[64] = {0};
+    const int dev = current_device() & 63;
+    if (!cached[dev]) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cs_sort_kernel<IT>, RS_THREADS, 0) != cudaSuccess) per_sm = 0;
+        cached[dev] = per_sm > 0 ? sm_count() : -1;            // one block per SM is all the sort needs
+    }
+    return cached[dev] > 0 ? cached[dev] : 0;
+}
+
+template <int IT>
+static int cs_launch(uint32_t *mask, int32_t *argsort, int64_t n, int passes, uint32_t *keys_a, int32_t *vals_a,
+                     uint32_t *keys_b, int32_t *vals_b, int *counts, int *totals, unsigned *bar, cudaStream_t stream) {
+    const int G = (int)div_up64(n, RS_THREADS * IT);
+    void *args[] = {&mask, &argsort, &n, &passes, &keys_a, &vals_a, &keys_b, &vals_b, &counts, &totals, &bar};
+    SPX_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)cs_sort_kernel<IT>, dim3(G), dim3(RS_THREADS), args, 0, stream));
+    count_launch();
+    return 0;
+}
+
 size_t radix_argsort_workspace_bytes(int64_t n) {
     const int64_t nblk = div_up64(n > 0 ? n : 1, RS_TILE);
     // legacy path: 2 count matrices + totals; onesweep: hist + tickets + per-pass status words (they share)
@@ -355,6 +512,21 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
     const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
     const uint32_t *kin = mask;
     const int32_t *vin = nullptr;
+    if ((runtime_cfg().debug & 512) && passes >= 2) {
+        // ---- cooperative: one launch for all passes when every tile's block can be co-resident
+        const int it = div_up64(n, RS_THREADS * 4) <= cs_max_blocks<4>() ? 4
+                     : (div_up64(n, RS_THREADS * 8) <= cs_max_blocks<8>() ? 8 : 0);
+        if (it) {
+            const int G = (int)div_up64(n, RS_THREADS * it);
+            int *counts = ws.take<int>((size_t)RS_BINS * G);
+            int *totals = ws.take<int>(RS_BINS);
+            unsigned *bar = ws.take<unsigned>(64);
+            SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
+            SPX_CHECK_CUDA(cudaMemsetAsync(bar, 0, 64 * sizeof(unsigned), stream));
+            return it == 4 ? cs_launch<4>(mask, argsort, n, passes, keys_a, vals_a, keys_b, vals_b, counts, totals, bar, stream)
+                           : cs_launch<8>(mask, argsort, n, passes, keys_a, vals_a, keys_b, vals_b, counts, totals, bar, stream);
+        }
+    }
     if (runtime_cfg().debug & 64) {
         // ---- onesweep: memset(scratch) + histogram of all passes + one kernel per pass
         const size_t head_ints = (size_t)OS_MAX_PASSES * RS_BINS + 64;        // hist[4][512] + tickets

@@ -16,7 +16,7 @@ for n in (100_000, 800_000):
     rng = np.random.default_rng(50051)
     inds = torch.from_numpy(surface_cloud(rng, shape, n if n <= 100_000 else 100_000, batch=max(1, n // 100_000))).to(dev)
     bs = max(1, n // 100_000)
-    for dbg, name in ((0, "two-kernel"), (64, "onesweep")):
+    for dbg, name in ((0, "two-kernel"), (512, "cooperative")):
         _cabi.check(_cabi.load().spx_debug_configure(-1, 0, dbg, None, 0), "cfg")
         acc = {}
         ref = None
@@ -40,7 +40,7 @@ shape4 = [41, 1440, 1440]
 rng = np.random.default_rng(50051)
 inds4 = torch.from_numpy(surface_cloud(rng, shape4, 300_000)).to(dev)
 keep = None
-for dbg, name in ((128, "legacy"), (0, "default")):
+for dbg, name in ((128, "legacy"), (0, "default"), (512, "default+coop")):
     _cabi.check(_cabi.load().spx_debug_configure(-1, 0, dbg, None, 0), "cfg")
     acc = {}
     for rep in range(6):
@@ -51,7 +51,7 @@ for dbg, name in ((128, "legacy"), (0, "default")):
         for k, v in timer.get_all_pair_time().items():
             acc.setdefault(k, []).append(v)
     print(f"conv k3s2 N=300000 M={res[0].shape[0]} {name:8s}", {k: round(float(np.median(v)) * 1e3, 1) for k, v in acc.items()}, "us")
-    if keep is None:
+    if name == "legacy":
         keep = [t.clone() for t in (res[0], res[2], res[3], res[6][0], res[7][0])]
     else:
         print("   identical to legacy:", all(bool(torch.equal(a, b)) for a, b in zip(keep, (res[0], res[2], res[3], res[6][0], res[7][0]))))
