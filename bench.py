@@ -86,6 +86,9 @@ def parse_args():
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
+    ap.add_argument("--debug-bits", type=int, default=0,
+                    help="spx_debug_configure bits for A/B runs (64 onesweep sort, 128 round-1 conv rulebook, "
+                         "512 cooperative sort); recorded in config.debug_bits")
     return ap.parse_args()
 
 
@@ -235,6 +238,9 @@ class Ctx:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+        if args.debug_bits:
+            from spconv_b200 import _cabi
+            _cabi.check(_cabi.load().spx_debug_configure(-1, 0, int(args.debug_bits), None, 0), "debug_configure")
         self.flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=self.dev)
         self.side = torch.cuda.Stream()
         self.side2 = torch.cuda.Stream()
@@ -931,7 +937,7 @@ def run_ours(args):
                        "parallelism": f"dp{world} (one batch per GPU)" + (
                            "; NCCL all-reduce(dW) of step i is captured at the head of step i+1's compute graph"
                            if world > 1 and head["cuda_graph"] else ("; NCCL all-reduce(dW) per step" if world > 1 else "")),
-                       "cuda_graph": head["cuda_graph"],
+                       "cuda_graph": head["cuda_graph"], "debug_bits": int(args.debug_bits),
                        "pipeline": (("rulebooks two clouds ahead on two alternating side streams (one rulebook + one "
                                      "fwd/dgrad/wgrad per timed step; a step waits for its own rulebook); "
                                      if head.get("pipelined") == 2 else
