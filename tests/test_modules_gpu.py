@@ -279,7 +279,9 @@ def test_graph_capture_of_a_subm_training_step(cuda_dev):
 
     f0 = torch.from_numpy(feats).to(cuda_dev).half()
     loss_e, grads_e = step(f0, d_inds)
-    loss_e, grads_e = loss_e.clone(), [g.clone() for g in grads_e]
+    # detach: a live autograd graph from an eager step keeps its AccumulateGrad nodes (bound to the
+    # stream they were created on) alive, and a capture must not touch the legacy default stream
+    loss_e, grads_e = loss_e.detach().clone(), [g.detach().clone() for g in grads_e]
     g = spconv.graph_capture(step, f0, d_inds)
     f1 = (f0 * 0.5).contiguous()
     g(f1, d_inds)                                        # different data, same shapes

@@ -195,8 +195,21 @@ def test_tile_table_from_row_table_matches_column_path(cuda_dev):
     shape = [24, 200, 176]
     inds = torch.from_numpy(surface_cloud(rng, shape, 9000 + 77)).to(cuda_dev)
     n = inds.shape[0]
-    res = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3,
-                                             [1] * 3, [1] * 3, [0] * 3, True, False, is_train=True)
+    # the fused native call (default) builds the table from the row-major by-product inside C; its cached
+    # result must equal what the separate calls produce from either source
+    fused = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3,
+                                               [1] * 3, [1] * 3, [0] * 3, True, False, is_train=True)
+    fused_cache = getattr(fused[6][0], "_spx_tile_cache", None)
+    assert fused_cache is not None, "the fused rulebook call must leave the tile table cached on the argsort"
+    old = ops.SPCONV_B200_FUSED_RULEBOOK
+    ops.SPCONV_B200_FUSED_RULEBOOK = False
+    try:
+        res = ops.get_indice_pairs_implicit_gemm(inds, 1, shape, ConvAlgo.MaskImplicitGemm, [3] * 3, [1] * 3,
+                                                 [1] * 3, [1] * 3, [0] * 3, True, False, is_train=True)
+    finally:
+        ops.SPCONV_B200_FUSED_RULEBOOK = old
+    for a, b in ((fused[2], res[2]), (fused[3], res[3]), (fused[4][0], res[4][0]), (fused[6][0], res[6][0])):
+        assert torch.equal(a, b)
     pair_fwd, mask, argsort = res[2], res[4][0], res[6][0]
     hint = getattr(argsort, "_spx_row_table", None)
     assert hint is not None, "3x3x3 SubM rulebook must hand the row-major table to the tile builder"
@@ -207,6 +220,7 @@ def test_tile_table_from_row_table_matches_column_path(cuda_dev):
     assert argsort._spx_row_table is None                       # consumed
     t_cols, m_cols = ops._tile_tables(pair_fwd, mask, argsort, n, 27, owner=None)
     assert torch.equal(t_rows, t_cols) and torch.equal(m_rows, m_cols)
+    assert torch.equal(fused_cache[1], t_cols) and torch.equal(fused_cache[2], m_cols)
     tiles = (n + 127) // 128
     flat = t_cols.cpu().numpy()
     tab = flat[:tiles * 28 * 128].reshape(tiles, 28, 128)

@@ -5,7 +5,7 @@ TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 echo "== session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60) > $O/${TAG}_tests.log
+(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -400) > $O/${TAG}_tests.log
 tail -6 $O/${TAG}_tests.log | cut -c1-300
 (timeout 100 python tools/host_profile.py cfg2 50 > $O/${TAG}_hostprof_cfg2.log 2>&1); head -1 $O/${TAG}_hostprof_cfg2.log
 (timeout 100 python tools/host_profile.py encoder 30 > $O/${TAG}_hostprof_enc.log 2>&1); head -1 $O/${TAG}_hostprof_enc.log
