@@ -80,7 +80,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the device-resident step from CUDA graphs")
-    ap.add_argument("--pipeline", type=int, default=1,
+    ap.add_argument("--pipeline", type=int, default=2,
                     help="software-pipeline the graph replay: 1 = rulebook of cloud i+1 beside the GEMMs of cloud i "
                          "(streams joined every step), 2 = rulebooks two clouds ahead on two side streams, 0 = serial")
     ap.add_argument("--extras", type=int, default=-1,
@@ -769,8 +769,8 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
             torch.cuda.synchronize()
 
     def e2e_step(i):
-        if e2e_graphs is None:
-            return e2e_step_eager(i)
+        if e2e_graphs is None:                      # not capturable: the pipelined eager loop IS the e2e path
+            return e2e_step_eager_pipe(i)
         e2e_graphs[i % NUM_CLOUDS].replay()
 
     # kernels of THIS library per step (graph replays re-issue exactly the captured launches)

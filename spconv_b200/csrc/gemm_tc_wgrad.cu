@@ -529,6 +529,10 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     p.groups_total = (atoms_total + p.apg - 1) / p.apg;
     p.groups_per_pass = 512 / a.c_out;
     if (p.groups_per_pass > 32) p.groups_per_pass = 32;
+    // A/B knob (spx_debug_configure bit 1024): half the accumulators per CTA => twice the passes, half the
+    // chunks.  The fp32 partial volume (chunks x all groups) halves, the dout tile is gathered by twice as
+    // many passes -- see profiles/README.md for the measured trade.
+    if ((runtime_cfg().debug & 1024) && p.groups_per_pass >= 2) p.groups_per_pass /= 2;
     pl.passes = (p.groups_total + p.groups_per_pass - 1) / p.groups_per_pass;
     p.a_stage_bytes = p.apg * WG_TILE * p.span_x;
     p.b_buf_bytes = WG_TILE * p.db;
