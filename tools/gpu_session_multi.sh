@@ -1,0 +1,24 @@
+#!/bin/bash
+# multi-GPU session: bash tools/gpu_session_multi.sh <tag> <N>
+TAG=${1:-r2n}; N=${2:-2}
+O=gpurun_out
+mkdir -p $O
+echo "== multi session $TAG N=$N $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name --format=csv,noheader | head -8
+run() {  # name, extra args
+  (timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 $2 > $O/${TAG}_$1.json 2> $O/${TAG}_$1.err)
+  tail -c 300 $O/${TAG}_$1.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$O/${TAG}_$1.json").read().strip().splitlines()[-1])
+    print("$1", "value", round(d["value"]/1e6,1), "M/s ms", round(d["ms_per_step"],4), "serial", d.get("serial_ms_per_step"), "e2e", round(d["e2e"]["ms_per_step"],4), "eager", round(d["e2e"]["eager_ms_per_step"],4))
+    for k,w in d.get("workloads",{}).items():
+        print("   ", k, w.get("error") or (round(w["value"]/1e6,1), round(w["ms_per_step"],4)))
+except Exception as e:
+    print("$1 FAILED", e)
+PY
+}
+run bench ""
+run bench_serial "--pipeline 0 --extras 0"
+(timeout 200 python bench.py --gpus 1 --extras 0 > $O/${TAG}_bench_n1.json 2>> $O/${TAG}_bench.err); python -c "import json; d=json.loads(open('$O/${TAG}_bench_n1.json').read().strip().splitlines()[-1]); print('N=1 same box', d['value']/1e6, d['ms_per_step'])"
+echo "== done $(date -u +%H:%M:%S)"
