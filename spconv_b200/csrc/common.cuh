@@ -302,6 +302,13 @@ __host__ __device__ __forceinline__ uint64_t smem_desc_hi(uint32_t lbo_bytes, ui
            (1ull << 46) | (layout << 61);
 }
 
+// same with an explicit layout code (1 = SWIZZLE_128B_BASE32B: 128-byte rows, 32-byte swizzle atoms -- the
+// MN-major layout of 32-bit operands)
+__host__ __device__ __forceinline__ uint64_t smem_desc_hi_layout(uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (layout << 61);
+}
+
 // Instruction descriptor, dense, no negate, no saturate.
 //   c_format: 0 f16, 1 f32, 2 s32;  ab_format: kind::f16 -> 0 f16 / 1 bf16; tf32 -> 2; i8 -> 1 (signed)
 __host__ __device__ __forceinline__ uint32_t make_idesc(int c_format, int a_format, int b_format, int a_mn_major,

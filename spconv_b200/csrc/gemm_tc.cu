@@ -56,6 +56,7 @@ struct TcParams {
     int q_a;                // k-steps (32 B) per A sub-tile = span_a / 32
     // weight operand B (TMA box = [b_rows x span_b bytes] per sub-tile)
     int span_b, b_subtiles, b_sub_bytes, b_bytes, b_mn_major, q_b, b_kstep16_mn;
+    int b_base32;           // 1: MN-major 32-bit B operand in the SWIZZLE_128B_BASE32B layout (tf32 input gradient)
     int w_inner_elems;      // c_in (elements between consecutive offsets along the TMA inner dim)
     int span_b_elems;       // span_b / elem bytes
     int n;                  // UMMA N (output channels of this pass)
@@ -409,8 +410,11 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams
         int nstamp = 0;
         int stage = 0; uint32_t phase = 0;
         const uint64_t a_hi = smem_desc_hi(16u, 8u * SPAN_A, SPAN_A);
-        const uint64_t b_hi = p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
-                                           : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
+        // MN-major B: LBO = distance between 128-byte column atoms, SBO = one swizzle atom of K rows
+        // (8 rows for the 16-byte-base swizzles, 4 rows for the 32-byte-base layout of 32-bit operands)
+        const uint64_t b_hi = p.b_base32 ? smem_desc_hi_layout((uint32_t)p.b_sub_bytes, 4u * p.span_b, 1ull)
+                              : p.b_mn_major ? smem_desc_hi((uint32_t)p.b_sub_bytes, 8u * p.span_b, p.span_b)
+                                             : smem_desc_hi(16u, 8u * p.span_b, p.span_b);
         const uint32_t b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
         for (int local = 0;; ++local) {
             uint32_t tm[4];
@@ -534,7 +538,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D view of the KRSC filter: inner = kv*c_in elements, outer = c_out rows
-int make_weight_tmap(CUtensorMap *tm, const void *w, int dtype, int kv, int c_in, int c_out, int span_bytes) {
+int make_weight_tmap(CUtensorMap *tm, const void *w, int dtype, int kv, int c_in, int c_out, int span_bytes,
+                     bool base32 = false) {
     EncodeTiledFn fn = get_encode_fn();
     SPX_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
     const int e = dtype_bytes(dtype);
@@ -546,7 +551,8 @@ int make_weight_tmap(CUtensorMap *tm, const void *w, int dtype, int kv, int c_in
     cuuint64_t strides[1] = {(cuuint64_t)kv * c_in * e};
     cuuint32_t box[2] = {(cuuint32_t)(span_bytes / e), (cuuint32_t)c_out};
     cuuint32_t estr[2] = {1, 1};
-    CUtensorMapSwizzle sw = span_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+    CUtensorMapSwizzle sw = base32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                          : span_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : span_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                              : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r = fn(tm, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -578,8 +584,10 @@ static bool tc_shape_ok(int dtype, int kv, int c_in, int c_out, int transpose_w)
 bool tc_gather_gemm_supported(const GatherGemmArgs &a) {
     if (a.dtype == SPX_I8) return false;
     if (!a.tile_table || !a.tile_mask) return false;   // built by spx_build_tile_table
-    // tf32 MN-major operands need the SWIZZLE_128B_BASE32B atom (not tiled here yet): fp32 dgrad -> SIMT
-    if (a.dtype == SPX_F32 && a.transpose_w) return false;
+    // tf32 input gradient: the filter box is an MN-major 32-bit operand = SWIZZLE_128B_BASE32B layout (TMA
+    // swizzle mode 128B_ATOM_32B).  Needs whole 128-byte filter rows; experimental until measured
+    // (spx_debug_configure bit 256), otherwise fp32 dgrad runs on the FMA kernel.
+    if (a.dtype == SPX_F32 && a.transpose_w && (!(runtime_cfg().debug & 256) || (a.c_in * 4) % 128)) return false;
     if (((size_t)a.kv * a.c_in * dtype_bytes(a.dtype)) % 16) return false;
     return tc_shape_ok(a.dtype, a.kv, a.c_in, a.c_out, a.transpose_w);
 }
@@ -607,6 +615,7 @@ static int fill_params(const GatherGemmArgs &a, TcParams &p) {
     p.b_mn_major = a.transpose_w;
     p.q_b = p.span_b / 32;
     p.b_kstep16_mn = ((32 / e) * p.span_b) >> 4;   // one k-step = UMMA_K rows of the weight box
+    p.b_base32 = (a.dtype == SPX_F32 && a.transpose_w) ? 1 : 0;
     p.w_inner_elems = a.c_in;
     p.span_b_elems = p.span_b / e;
     p.n = cy;
@@ -688,7 +697,7 @@ int tc_gather_gemm(const GatherGemmArgs &a, cudaStream_t stream) {
     if (fill_params(a, p)) return 2;
     if (copy_mask_out(a, stream)) return 1;
     CUtensorMap tm;
-    if (make_weight_tmap(&tm, a.w, a.dtype, a.kv, a.c_in, a.c_out, p.span_b)) return 2;
+    if (make_weight_tmap(&tm, a.w, a.dtype, a.kv, a.c_in, a.c_out, p.span_b, p.b_base32 != 0)) return 2;
     if (a.dtype == SPX_F32) return launch_tc<KIND_TF32>(tm, p, stream);
     return launch_tc<KIND_F16>(tm, p, stream);
 }

@@ -408,3 +408,34 @@ def test_int8_forward_at_config5_size(oracle, cuda_dev):
     assert 0.05 < (got > 0).mean() < 0.95 and got.max() == 127            # the clip and the ReLU are both exercised
     diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (diff.max(), (diff > 0).mean())
+
+
+@pytest.mark.xfail(reason="experimental tcgen05 tf32 MN-major operand layout: off by default until validated on the GPU",
+                   strict=False)
+def test_tf32_input_gradient_on_tensor_cores(oracle, cuda_dev, monkeypatch):
+    """fp32 + SPCONV_ALLOW_TF32: the input gradient on tcgen05 (kind::tf32, filter consumed as an MN-major
+    SWIZZLE_128B_BASE32B operand).  Experimental path behind spx_debug_configure bit 256."""
+    from spconv_b200 import _cabi
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch import ops
+    monkeypatch.setattr(ops, "SPCONV_ALLOW_TF32", True)
+    lib = _cabi.load()
+    _cabi.check(lib.spx_debug_configure(-1, 0, 256, None, 0), "debug_configure")
+    try:
+        for C, K, subm in ((32, 64, True), (64, 64, True), (64, 32, False)):
+            s = _setup(oracle, cuda_dev, "f32", C, K, subm, stride=1 if subm else 2)
+            inds = torch.from_numpy(s["inds"]).to(cuda_dev)
+            res = ops.get_indice_pairs_implicit_gemm(inds, s["bs"], s["shape"], ConvAlgo.MaskImplicitGemm, s["ks"], s["st"],
+                                                     s["pd"], s["dl"], [0] * 3, subm, False, is_train=True)
+            m = res[0].shape[0]
+            x = torch.from_numpy(s["feats"]).to(cuda_dev)
+            w = torch.from_numpy(s["w"]).to(cuda_dev)
+            rng = np.random.default_rng(3)
+            dout = rng.uniform(-1, 1, size=(m, K)).astype(np.float32)
+            din, dw = ops.implicit_gemm_backward(x, w, torch.from_numpy(dout).to(cuda_dev), res[2], res[3], res[4], res[5],
+                                                 res[6], res[7], None, res[8], 128, subm)
+            ref_din, ref_dw = oracle.indice_conv_backward(s["feats"], s["w"], dout, s["pairs"], s["num"], False, subm)
+            assert rel_l2(din.cpu().numpy(), ref_din) < 2e-3, describe_mismatch(din.cpu().numpy(), ref_din, f"tf32 din C{C}K{K}")
+            assert rel_l2(dw.cpu().numpy(), ref_dw) < 2e-3
+    finally:
+        _cabi.check(lib.spx_debug_configure(-1, 0, 0, None, 0), "debug_configure")
