@@ -638,6 +638,18 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
                                                     _ptr(dfilters), ws.data_ptr(), ws.numel(),
                                                     _stream()), "implicit_gemm_wgrad")
 
+    if _WGRAD_HOOK is not None and n_in and n_out:
+        # Data-parallel overlap: weight gradient FIRST, then the hook (typically the all-reduce of dW) on
+        # a forked stream while the input gradient -- which the hook does not need -- runs on this one.
+        main = torch.cuda.current_stream()
+        side = _side_stream(features.device)
+        run_wgrad()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _WGRAD_HOOK(dfilters)
+        run_dgrad()
+        main.wait_stream(side)
+        return din, dfilters
     if timer.enable or not (n_in and n_out) or not torch._C._cuda_isCurrentStreamCapturing():
         # eager launches are host-bound (and an eager fork/join per call measured slower, not
         # faster); profiling regions stay one kernel each
@@ -656,6 +668,19 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         run_dgrad()
     main.wait_stream(side)
     return din, dfilters
+
+
+_WGRAD_HOOK = None
+
+
+def set_wgrad_hook(fn) -> None:
+    """``fn(dfilters)`` is called on a forked stream right after every weight-gradient launch of
+    :func:`implicit_gemm_backward`, while the input gradient of the same layer runs on the caller's
+    stream (joined before the op returns).  This is the place for a data-parallel all-reduce of the
+    layer's dW: it overlaps the rest of the backward pass instead of trailing it (DDP-style hook).
+    ``None`` removes the hook."""
+    global _WGRAD_HOOK
+    _WGRAD_HOOK = fn
 
 
 # ---------------------------------------------------------------------------- ConvAlgo.Native
