@@ -167,10 +167,17 @@ struct P2VWs {
 };
 
 static size_t p2v_sort_tmp(int64_t n) {
+    // The size query goes through the CUDA runtime: a stale error left by an earlier failed call (e.g. a
+    // refused stream capture) would make it return early with bytes = 0, and the workspace computed here
+    // would then be smaller than what the same query yields a moment later.  Clear the state first and
+    // never return less than a bound that covers CUB's double buffers + histograms.
+    cudaGetLastError();
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-    return bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    const size_t floor_bytes = (size_t)(n > 0 ? n : 1) * 16 + (1u << 20);
+    if (e != cudaSuccess) { cudaGetLastError(); return floor_bytes; }
+    return bytes > floor_bytes ? bytes : floor_bytes;
 }
 
 static bool p2v_i64(const int *grid, int ndim) {

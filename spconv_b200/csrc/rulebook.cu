@@ -921,10 +921,17 @@ extern "C" int64_t spx_conv_max_out(const spx_conv_geometry *g, int64_t num_in) 
 }
 
 static size_t sort_pairs_temp_bytes(int64_t n) {
+    // The size query goes through the CUDA runtime: a stale error left by an earlier failed call (e.g. a
+    // refused stream capture) would make it return early with bytes = 0, and the workspace computed here
+    // would then be smaller than what the same query yields a moment later.  Clear the state first and
+    // never return less than a bound that covers CUB's double buffers + histograms.
+    cudaGetLastError();
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-    return bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    const size_t floor_bytes = (size_t)(n > 0 ? n : 1) * 16 + (1u << 20);
+    if (e != cudaSuccess) { cudaGetLastError(); return floor_bytes; }
+    return bytes > floor_bytes ? bytes : floor_bytes;
 }
 
 extern "C" size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_t num_in, int64_t max_out, int is_subm) {

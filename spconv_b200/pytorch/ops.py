@@ -605,9 +605,14 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
             di, dw = implicit_gemm_backward(features, filters, out_bp, pair_fwd, pair_bwd,
                                             [pair_mask_fwd_splits[j]], bwd_m, [mask_argsort_fwd_splits[j]],
                                             bwd_s, None, masks, mask_width, is_subm, timer, fp32_accum)
+            # dW of split j is only meaningful on ITS offsets: the tcgen05 kernel leaves the others zero, the
+            # generic FMA kernel (odd channel counts) walks the whole pair table -- mask either way
+            keep = torch.tensor([(int(masks[j][k >> 5]) >> (k & 31)) & 1 for k in range(kv)], dtype=dw.dtype,
+                                device=dw.device).view(1, kv, 1)
+            dw = dw.view(c_out, kv, c_in) * keep
             din = di if din is None else din.add_(di)
             dfilters = dw if dfilters is None else dfilters.add_(dw)
-        return din, dfilters
+        return din, dfilters.view(filters.shape)
     din = torch.empty_like(features)
     dfilters = torch.empty_like(filters)
     mask_fwd, argsort_fwd = _first(pair_mask_fwd_splits), _first(mask_argsort_fwd_splits)
