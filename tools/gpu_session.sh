@@ -10,9 +10,6 @@ tail -6 $O/${TAG}_tests.log | cut -c1-300
 (timeout 100 python tools/host_profile.py cfg2 50 > $O/${TAG}_hostprof_cfg2.log 2>&1); head -1 $O/${TAG}_hostprof_cfg2.log
 (timeout 100 python tools/host_profile.py encoder 30 > $O/${TAG}_hostprof_enc.log 2>&1); head -1 $O/${TAG}_hostprof_enc.log
 (timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
-(timeout 200 python bench.py --extras 0 --debug-bits 1024 > $O/${TAG}_bench_gpp.json 2>> $O/${TAG}_bench.err); python -c "import json,sys; d=json.loads(open('$O/${TAG}_bench_gpp.json').read().strip().splitlines()[-1]); print('wgrad-gpp/2 value', d['value'], d['ms_per_step'], 'serial', d.get('serial_ms_per_step'), d['kernel_ms'])"
-(timeout 200 python bench.py --extras 0 --debug-bits 512 > $O/${TAG}_bench_coop.json 2>> $O/${TAG}_bench.err); python -c "import json,sys; d=json.loads(open('$O/${TAG}_bench_coop.json').read().strip().splitlines()[-1]); print('coop-sort value', d['value'], d['ms_per_step'], 'serial', d.get('serial_ms_per_step'))"
 (timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err); head -c 200 $O/${TAG}_bench_reference.json; echo
-(timeout 120 python tools/ab_rulebook.py > $O/${TAG}_ab_rulebook.log 2>&1); tail -12 $O/${TAG}_ab_rulebook.log | cut -c1-250
 (timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches.csv python bench.py --graph 0 --extras 0 --steps 2 --warmup 1 > $O/${TAG}_ncu_bench.log 2>&1); tail -1 $O/${TAG}_ncu_bench.log | cut -c1-120
 echo "== done $(date -u +%H:%M:%S)"
