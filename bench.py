@@ -868,6 +868,12 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
                 "eager_prefetch_ms_per_step": ms_e2e_eager, "eager_naive_ms_per_step": ms_e2e_naive},
         "clocks": clocks,
         "kernel_ms": {k: round(v, 4) for k, v in sorted(regions.items())},
+        # rulebook generation (hash / rank / mask sort / tile tables) vs the GEMM kernels, summed over the layers;
+        # a rulebook shared through an indice_key is built once and so counted once
+        "kernel_ms_summary": {
+            "rulebook": round(sum(v for k, v in regions.items() if "gen_" in k or "tile_table" in k), 4),
+            "gemm_fwd": round(sum(v for k, v in regions.items() if k.split(".")[-1] in ("implicit_gemm", "implicit_gemm_int8")), 4),
+            "gemm_bwd": round(sum(v for k, v in regions.items() if k.split(".")[-1] in ("implicit_gemm_dgrad", "implicit_gemm_wgrad")), 4)},
         "config": w.config(),
     }
     if ms_reuse is not None:
@@ -978,6 +984,8 @@ def run_ours(args):
             "gpu_launches": int(head["launches_per_step"] * args.steps),
             "clocks": head["clocks"],
             "kernel_ms": head["kernel_ms"],
+            "kernel_ms_summary": head["kernel_ms_summary"],
+            "allreduce": head["allreduce"],
             "roofline": head["roofline"],
         }
         if "indice_key_reuse" in head:
