@@ -434,7 +434,12 @@ class EncoderWorkload(Workload):
         for m in self.layers:
             m.train()
         self.bucket = GradBucket([m.weight for m in self.layers])
-        self.prefetcher = ctx.spconv.RulebookPrefetcher([self.layers[0]], stream=ctx.side)
+        # every layer's rulebook (the strided ones included) is built ahead of the step that uses it,
+        # on the side stream, by a worker thread: the output-count read-backs of the three regular
+        # convs then wait for rulebook kernels only, never for the GEMM queue of the training stream.
+        self.pipelined = bool(ctx.args.pipeline)
+        self.prefetcher = ctx.spconv.RulebookPrefetcher(self.layers, stream=ctx.side, background=self.pipelined)
+        self.staged = {}
         self.layer_stats = None
 
     def make_input(self, d_inds, d_feats, timer=None):
@@ -469,7 +474,20 @@ class EncoderWorkload(Workload):
         return loss
 
     def device_step(self, c, timer=None):
-        self.forward_backward(c["d_inds"], c["d_feats"], timer)
+        if timer is not None or not self.pipelined:
+            self.forward_backward(c["d_inds"], c["d_feats"], timer)
+            return self.bucket.flat
+        # rulebooks one cloud ahead: this step consumes the chain staged by the previous step (or builds
+        # it now, first step of a loop) and starts the next cloud's chain before issuing its own GEMMs.
+        # Each timed step = one full 5-rulebook chain + one 6-layer forward + backward.
+        ci = self.clouds.index(c)
+        x = self.staged.pop(ci, None)
+        if x is None:
+            x = self.prefetcher.prefetch(self.make_input(c["d_inds"], c["d_feats"]), wait_current=False)
+        nxt = (ci + 1) % len(self.clouds)
+        cn = self.clouds[nxt]
+        self.staged[nxt] = self.prefetcher.prefetch(self.make_input(cn["d_inds"], cn["d_feats"]), wait_current=False)
+        self.forward_backward(None, None, x=self.prefetcher.ready(x))
         return self.bucket.flat
 
     def grads(self):

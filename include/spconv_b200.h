@@ -338,7 +338,7 @@ int spx_implicit_gemm_fwd_int8(const spx_gemm_desc *d, const int8_t *features,
 /* which kernel family served the last call of each kind on this thread: 0 none, 1 SIMT,
  * 2 tcgen05.  Used by tests/bench to prove the tensor-core path ran. */
 int spx_last_kernel_family(void);
-/* number of kernel launches issued by this library on the calling thread since the last reset */
+/* number of kernel launches issued by this library (all host threads) since the last reset */
 int64_t spx_launch_count(int reset);
 /*
  * Test / perf-triage switches (never needed for correct operation; the reference's counterpart is
@@ -347,7 +347,9 @@ int64_t spx_launch_count(int reset);
  *                 shape does not tile) -- the start-up value comes from SPX_FORCE_SIMT / SPX_FORCE_TC,
  *                 read once when the library is loaded;
  *   tc_ctas:      0 keep, 1 or 2 resident CTAs per SM for the forward / dgrad kernel;
- *   debug_bits:   ablation mask of the tcgen05 kernels (results are wrong by construction when set);
+ *   debug_bits:   A/B and ablation mask (bits 1..32: ablations of the tcgen05 kernels, results are wrong by
+ *                 construction; 64 / 512: alternative sorts; 128: legacy regular-conv rulebook; 256: fp32+TF32
+ *                 input gradient on the FMA kernel instead of tcgen05; 1024: weight-gradient pass split);
  *   trace_buf:    NULL or a DEVICE buffer of at least 8*2048 int64 that receives clock stamps.
  */
 int spx_debug_configure(int force_family, int tc_ctas, int debug_bits, void *trace_buf,

@@ -1,12 +1,13 @@
-// Library core: thread-local error string, launch counter, device check, elementwise epilogue.
+// Library core: thread-local error string, process-wide launch counter, device check, elementwise epilogue.
 #include "common.cuh"
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 
 namespace spx {
 
 static thread_local char g_err[1024] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: a prefetch thread's launches count too
 static thread_local int g_family = 0;
 
 void set_error(const char *fmt, ...) {
@@ -15,7 +16,7 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void set_family(int f) { g_family = f; }
 
 int current_device() {
@@ -87,9 +88,7 @@ extern "C" const char *spx_last_error(void) { return g_err; }
 extern "C" int spx_version(void) { return 100; }
 extern "C" int spx_last_kernel_family(void) { return g_family; }
 extern "C" int64_t spx_launch_count(int reset) {
-    int64_t v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
 extern "C" int spx_debug_configure(int force_family, int tc_ctas, int debug_bits, void *trace_buf, size_t trace_bytes) {

@@ -585,9 +585,9 @@ bool tc_gather_gemm_supported(const GatherGemmArgs &a) {
     if (a.dtype == SPX_I8) return false;
     if (!a.tile_table || !a.tile_mask) return false;   // built by spx_build_tile_table
     // tf32 input gradient: the filter box is an MN-major 32-bit operand = SWIZZLE_128B_BASE32B layout (TMA
-    // swizzle mode 128B_ATOM_32B).  Needs whole 128-byte filter rows; experimental until measured
-    // (spx_debug_configure bit 256), otherwise fp32 dgrad runs on the FMA kernel.
-    if (a.dtype == SPX_F32 && a.transpose_w && (!(runtime_cfg().debug & 256) || (a.c_in * 4) % 128)) return false;
+    // swizzle mode 128B_ATOM_32B).  Needs whole 128-byte filter rows, otherwise fp32 dgrad runs on the FMA
+    // kernel; spx_debug_configure bit 256 switches the tensor-core route off (A/B against the FMA kernel).
+    if (a.dtype == SPX_F32 && a.transpose_w && ((runtime_cfg().debug & 256) || (a.c_in * 4) % 128)) return false;
     if (((size_t)a.kv * a.c_in * dtype_bytes(a.dtype)) % 16) return false;
     return tc_shape_ok(a.dtype, a.kv, a.c_in, a.c_out, a.transpose_w);
 }

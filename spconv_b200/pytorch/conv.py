@@ -176,6 +176,19 @@ class SparseConvolution(SparseModule):
             raise ValueError(f"subm with same indice_key must have same num of indices, "
                              f"expect {datas.indices.shape[0]}, input {inp.indices.shape[0]}")
 
+    def _check_prefetched_valid(self, inp: SparseConvTensor, datas):
+        """A strided conv may only consume a rulebook that RulebookPrefetcher built for exactly this
+        layer geometry and this input coordinate set."""
+        assert getattr(datas, "prefetched", False), "only support reuse subm indices"
+        same = (self.kernel_size == datas.ksize and self.stride == datas.stride and self.padding == datas.padding
+                and self.dilation == datas.dilation and inp.spatial_shape == datas.spatial_shape
+                and inp.indices.shape[0] == datas.indices.shape[0]
+                and inp.indices.data_ptr() == datas.indices.data_ptr())
+        if not same:
+            raise ValueError(f"prefetched rulebook of indice_key {self.indice_key} does not match this layer / input: "
+                             f"expect ksize {datas.ksize} stride {datas.stride} padding {datas.padding} dilation "
+                             f"{datas.dilation} on {datas.indices.shape[0]} voxels in {datas.spatial_shape}")
+
     def _check_inverse_reuse_valid(self, inp: SparseConvTensor, spatial_shape: List[int], datas):
         if self.kernel_size != datas.ksize:
             raise ValueError(f"Inverse with same indice_key must have same kernel size, "
@@ -313,8 +326,10 @@ class SparseConvolution(SparseModule):
                 mask_fwd, mask_bwd = datas.pair_mask_fwd_splits, datas.pair_mask_bwd_splits
                 sort_fwd, sort_bwd = datas.mask_argsort_fwd_splits, datas.mask_argsort_bwd_splits
                 masks = datas.masks
-                assert self.subm, "only support reuse subm indices"
-                self._check_subm_reuse_valid(input, spatial_shape, datas)
+                if self.subm:
+                    self._check_subm_reuse_valid(input, spatial_shape, datas)
+                else:
+                    self._check_prefetched_valid(input, datas)
             else:
                 with timer.namespace("gen_pairs"):
                     try:

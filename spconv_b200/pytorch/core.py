@@ -147,6 +147,9 @@ class ImplicitGemmIndiceData:
     padding: List[int] = field(default_factory=list)
     in_voxel_num: Optional[Any] = None
     out_voxel_num: Optional[Any] = None
+    # built ahead of the forward pass by RulebookPrefetcher: the only case in which a strided conv may
+    # pick its rulebook up from the indice_dict (the reference lets SubM layers alone reuse a key)
+    prefetched: bool = False
 
 
 def scatter_nd(indices: torch.Tensor, updates: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:

@@ -311,7 +311,7 @@ def test_rulebook_prefetch_on_a_side_stream(cuda_dev):
                                   spconv.SparseConv3d(64, 64, 3, 2, 1, bias=False),
                                   spconv.SubMConv3d(64, 64, 3, bias=False, indice_key="b")).to(cuda_dev).half()
     pre = spconv.RulebookPrefetcher(net)
-    assert [m.indice_key for m in pre.layers] == ["a"]           # "b" lives behind the strided layer
+    assert [m.indice_key for m in pre.layers] == ["a", "a"]      # the keyless strided layer ends the chain
     f = torch.from_numpy(feats).to(cuda_dev).half()
     i = torch.from_numpy(inds).to(cuda_dev)
     ref = net(spconv.SparseConvTensor(f, i, shape, 1))
@@ -326,3 +326,52 @@ def test_rulebook_prefetch_on_a_side_stream(cuda_dev):
     n_plain = ops.launch_count(reset=True)
     assert torch.equal(y.features, ref.features) and torch.equal(y.indices, ref.indices)
     assert n_prefetched < n_plain                                  # the SubM "a" rulebook kernels are gone
+
+
+def test_rulebook_prefetch_follows_strided_layers_from_a_worker_thread(cuda_dev):
+    """Full-chain prefetch: every keyed layer's rulebook -- the strided ones too, whose output-count
+    read-back then happens on the prefetch stream in a worker thread -- is built ahead; the forward pass
+    launches no rulebook kernel, results and gradients equal the plain run; a strided layer refuses a
+    cached rulebook that was not prefetched for its geometry."""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.pytorch import ops
+    from bench_utils import make_encoder6
+    rng = np.random.default_rng(29)
+    shape = [32, 48, 40]
+    feats, inds = random_cloud(rng, shape, [2500, 1800], 16)
+    layers = [m.to(cuda_dev).half() for m in make_encoder6(spconv)]
+    net = spconv.SparseSequential(*layers)
+    pre = spconv.RulebookPrefetcher(net, background=True)
+    assert [m.indice_key for m in pre.layers] == ["subm1", "subm1", "down1", "subm2", "down2", "down3"]
+    i = torch.from_numpy(inds).to(cuda_dev)
+
+    def run(x):
+        for m in layers:
+            m.weight.grad = None
+        y = net(x)
+        (y.features.float().square().mean() * 64).backward()
+        return y, [m.weight.grad.clone() for m in layers], x.features.grad.clone()
+
+    f = torch.from_numpy(feats).to(cuda_dev).half()
+    y0, gw0, gx0 = run(spconv.SparseConvTensor(f.clone().requires_grad_(True), i, shape, 2))
+    ops.launch_count(reset=True)
+    run(spconv.SparseConvTensor(f.clone().requires_grad_(True), i, shape, 2))
+    n_plain = ops.launch_count(reset=True)
+
+    for _ in range(3):                                             # steady state: prefetch, then consume
+        x = pre.prefetch(spconv.SparseConvTensor(f.clone().requires_grad_(True), i, shape, 2))
+        x = pre.ready(x)
+        assert set(x.indice_dict) == {"subm1", "down1", "subm2", "down2", "down3"}
+        n_rulebook = ops.launch_count(reset=True)
+        y1, gw1, gx1 = run(x)
+        n_gemm = ops.launch_count(reset=True)
+        assert torch.equal(y1.indices, y0.indices) and torch.equal(y1.features, y0.features)
+        assert torch.equal(gx1, gx0) and all(torch.equal(a, b) for a, b in zip(gw1, gw0))
+        assert n_rulebook > 0 and n_rulebook + n_gemm == n_plain   # same kernels, moved ahead of the step
+    pre.shutdown()
+
+    # a strided layer with somebody else's key: cached, but not prefetched for this geometry
+    x = spconv.RulebookPrefetcher(net).prefetch(spconv.SparseConvTensor(f, i, shape, 2))
+    other = spconv.SparseConv3d(16, 32, 3, stride=1, padding=1, bias=False, indice_key="down1").to(cuda_dev).half()
+    with pytest.raises(ValueError, match="does not match this layer"):
+        other(x)
