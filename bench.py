@@ -85,6 +85,8 @@ def parse_args():
                          "(streams joined every step), 2 = rulebooks two clouds ahead on two side streams, 0 = serial")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: dW all-reduce fused into the weight-gradient kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
     ap.add_argument("--debug-bits", type=int, default=0,
                     help="spx_debug_configure bits for A/B runs (64 onesweep sort, 128 round-1 conv rulebook, "
@@ -241,6 +243,21 @@ class Ctx:
         if args.debug_bits:
             from spconv_b200 import _cabi
             _cabi.check(_cabi.load().spx_debug_configure(-1, 0, int(args.debug_bits), None, 0), "debug_configure")
+        # N > 1: the all-reduce of dW is the tail of the weight-gradient kernel (NVLink peer stores, csrc/peer.cu);
+        # --allreduce nccl keeps the library collective for A/B.  All ranks agree on which one runs.
+        self.peers = None
+        if self.world > 1 and args.allreduce == "fused":
+            from spconv_b200.pytorch.dist import PeerGroup
+            ok = torch.ones(1, device=self.dev, dtype=torch.int32)
+            try:
+                self.peers = PeerGroup(capacity_bytes=8 << 20, average=False)
+            except Exception as e:          # no peer mapping on this box: every rank falls back together
+                print(f"[bench] rank {self.rank}: fused all-reduce unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.peers = None
         self.flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=self.dev)
         self.side = torch.cuda.Stream()
         self.side2 = torch.cuda.Stream()
@@ -480,7 +497,7 @@ class EncoderWorkload(Workload):
         # rulebooks one cloud ahead: this step consumes the chain staged by the previous step (or builds
         # it now, first step of a loop) and starts the next cloud's chain before issuing its own GEMMs.
         # Each timed step = one full 5-rulebook chain + one 6-layer forward + backward.
-        ci = self.clouds.index(c)
+        ci = next(j for j, cj in enumerate(self.clouds) if cj is c)
         x = self.staged.pop(ci, None)
         if x is None:
             x = self.prefetcher.prefetch(self.make_input(c["d_inds"], c["d_feats"]), wait_current=False)
@@ -585,9 +602,12 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     world = ctx.world
     clouds = w.clouds
     train = not w.inference
-    if world > 1 and train and hasattr(w, "install_allreduce_hook"):
+    fused_ar = world > 1 and train and ctx.peers is not None
+    if fused_ar:
+        ops.set_peer_group(ctx.peers)            # every dW leaves its kernel already summed over the ranks
+    elif world > 1 and train and hasattr(w, "install_allreduce_hook"):
         w.install_allreduce_hook()               # all-reduce(dW) beside the input gradient of the same step
-    explicit_ar = world > 1 and train and not getattr(w, "hooked", False)
+    explicit_ar = world > 1 and train and not fused_ar and not getattr(w, "hooked", False)
 
     # ---------------- warm-up (also configures kernels / NCCL before any graph capture)
     for i in range(max(warmup, 3)):
@@ -900,9 +920,12 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
                                    "value_per_call": voxels * calls / (ms_reuse_r * 1e-3),
                                    "note": "one rulebook + tile tables, then fwd+bwd of two layers that share it"}
     res["roofline"] = roofline_of(w, regions)
-    res["allreduce"] = ("hook: right after the weight-gradient kernel, beside the input gradient (ops.set_wgrad_hook)"
-                        if getattr(w, "hooked", False) else ("one flat bucket after backward" if explicit_ar else "none"))
+    res["allreduce"] = ("fused: tail of the weight-gradient reduction kernel (fp32 slices pushed to every rank's exchange "
+                        "buffer over NVLink peer memory, summed locally in rank order; csrc/peer.cu)" if fused_ar else
+                        "NCCL hook: right after the weight-gradient kernel, beside the input gradient (ops.set_wgrad_hook)"
+                        if getattr(w, "hooked", False) else ("NCCL: one flat bucket after backward" if explicit_ar else "none"))
     ops.set_wgrad_hook(None)
+    ops.set_peer_group(None)
     return res
 
 

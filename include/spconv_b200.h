@@ -253,6 +253,46 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
                             void *dfilters, void *workspace, size_t workspace_bytes,
                             spx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel weight-gradient exchange over NVLink peer memory.  The reference has no
+ * distributed code: users wrap it in torch DDP, i.e. an NCCL all-reduce of dW after the backward
+ * pass.  Here the all-reduce is the tail of the weight-gradient kernel itself (csrc/peer.cu): every
+ * rank pushes its fp32 slice sums into every rank's exchange buffer and reduces the world's slices
+ * locally, in rank order, so all replicas end with bit-identical gradients after one rounding.
+ *
+ * Set-up (once per process group; the host side passes the 64-byte handles around, e.g. with
+ * torch.distributed.all_gather_object): every rank creates its buffer, opens the others', and fills
+ * a spx_peer_group with the addresses AS MAPPED IN ITS OWN PROCESS (buffers[rank] = its own).
+ * Calls on one group must be stream-ordered on each rank and issued in the same order on all ranks.
+ */
+#define SPX_MAX_PEERS 16
+typedef struct spx_peer_group {
+    int world, rank;
+    int timeout_ms;                 /* a peer that does not arrive in time: NaN result + spx_peer_error (0 = 20 s) */
+    int reserved;
+    uint64_t capacity_bytes;        /* largest exchanged tensor, as fp32 (what spx_peer_buffer_create got) */
+    void *buffers[SPX_MAX_PEERS];   /* exchange buffer of every rank */
+} spx_peer_group;
+
+size_t spx_peer_buffer_bytes(size_t capacity_bytes, int world);
+int spx_peer_buffer_create(size_t capacity_bytes, int world, void **buffer, unsigned char handle[64]);
+int spx_peer_buffer_open(const unsigned char handle[64], void **mapped);
+int spx_peer_buffer_close(void *mapped);
+int spx_peer_buffer_destroy(void *buffer);
+/* sticky error word of this rank's buffer (1 = a peer timed out); synchronous copy */
+int spx_peer_error(const spx_peer_group *pg, int *error);
+
+/* dfilters = scale * sum over ranks of this rank's weight gradient (see spx_implicit_gemm_wgrad); one
+ * rounding, identical bits on every rank.  Shapes the tcgen05 kernel does not tile fall back to the
+ * FMA weight gradient followed by spx_peer_allreduce. */
+int spx_implicit_gemm_wgrad_allreduce(const spx_gemm_desc *d, const void *features, const void *out_bp,
+                                      void *dfilters, void *workspace, size_t workspace_bytes,
+                                      const spx_peer_group *pg, float scale, spx_stream_t stream);
+/* data = scale * sum over ranks of data, in place (bias gradients and other small tensors);
+ * dtype SPX_F32 / SPX_F16 / SPX_BF16 */
+int spx_peer_allreduce(const spx_peer_group *pg, void *data, int64_t count, int dtype, float scale,
+                       spx_stream_t stream);
+
 /* x[r, j] = act(x[r, j] + bias[j])   in place; bias may be NULL */
 int spx_bias_act_inplace(void *x, const void *bias, int64_t rows, int cols, int dtype, int act,
                          float act_alpha, spx_stream_t stream);

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
-                    c_uint32, c_void_p)
+                    c_ubyte, c_uint32, c_uint64, c_void_p)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libspconv_b200.so")
@@ -38,6 +38,18 @@ class GemmDesc(Structure):
         ("mask", c_void_p), ("argsort", c_void_p),
         ("reverse_offsets", c_int),
         ("tile_table", c_void_p), ("tile_mask", c_void_p),
+    ]
+
+
+SPX_MAX_PEERS = 16
+
+
+class PeerGroup(Structure):
+    """``spx_peer_group``: the exchange buffers of a data-parallel group as mapped in this process."""
+    _fields_ = [
+        ("world", c_int), ("rank", c_int), ("timeout_ms", c_int), ("reserved", c_int),
+        ("capacity_bytes", c_uint64),
+        ("buffers", c_void_p * SPX_MAX_PEERS),
     ]
 
 
@@ -81,6 +93,15 @@ SIGNATURES = {
     "spx_implicit_gemm_wgrad_workspace_size": (c_size_t, [POINTER(GemmDesc)]),
     "spx_implicit_gemm_wgrad": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),
+    "spx_peer_buffer_bytes": (c_size_t, [c_size_t, c_int]),
+    "spx_peer_buffer_create": (c_int, [c_size_t, c_int, POINTER(c_void_p), POINTER(c_ubyte)]),
+    "spx_peer_buffer_open": (c_int, [POINTER(c_ubyte), POINTER(c_void_p)]),
+    "spx_peer_buffer_close": (c_int, [c_void_p]),
+    "spx_peer_buffer_destroy": (c_int, [c_void_p]),
+    "spx_peer_error": (c_int, [POINTER(PeerGroup), POINTER(c_int)]),
+    "spx_implicit_gemm_wgrad_allreduce": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                                  POINTER(PeerGroup), c_float, c_void_p]),
+    "spx_peer_allreduce": (c_int, [POINTER(PeerGroup), c_void_p, c_int64, c_int, c_float, c_void_p]),
     "spx_bias_act_inplace": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float,
                                      c_void_p]),
     "spx_implicit_gemm_fwd_int8": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p,

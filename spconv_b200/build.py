@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(_PKG, "lib")
 OBJ_DIR = os.path.join(_PKG, "lib", "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libspconv_b200.so")
 
-SOURCES = ["core.cu", "rulebook.cu", "sort.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_wgrad.cu", "api_gemm.cu", "pool.cu", "pointops.cu"]
+SOURCES = ["core.cu", "rulebook.cu", "sort.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_wgrad.cu", "api_gemm.cu", "pool.cu", "pointops.cu", "peer.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,6 +1,7 @@
 // C-ABI entry points of the conv arithmetic: validation + dispatch between the tcgen05
 // kernels (gemm_tc.cu) and the generic fp32-FMA kernels (gemm_simt.cu).
 #include "gemm.cuh"
+#include "peer.cuh"
 #include <stdlib.h>
 
 using namespace spx;
@@ -96,20 +97,37 @@ extern "C" size_t spx_implicit_gemm_wgrad_workspace_size(const spx_gemm_desc *d)
     return 256;
 }
 
+static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void *out_bp, void *dfilters, void *workspace,
+                       size_t workspace_bytes, const spx_peer_group *pg, float scale, spx_stream_t stream);
+
 extern "C" int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const void *out_bp,
                                        void *dfilters, void *workspace, size_t workspace_bytes,
                                        spx_stream_t stream) {
+    return wgrad_entry(d, features, out_bp, dfilters, workspace, workspace_bytes, nullptr, 1.f, stream);
+}
+
+extern "C" int spx_implicit_gemm_wgrad_allreduce(const spx_gemm_desc *d, const void *features, const void *out_bp,
+                                                 void *dfilters, void *workspace, size_t workspace_bytes,
+                                                 const spx_peer_group *pg, float scale, spx_stream_t stream) {
+    SPX_REQUIRE(pg != nullptr, "implicit_gemm_wgrad_allreduce: peer group is NULL");
+    return wgrad_entry(d, features, out_bp, dfilters, workspace, workspace_bytes, pg, scale, stream);
+}
+
+static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void *out_bp, void *dfilters, void *workspace,
+                       size_t workspace_bytes, const spx_peer_group *pg, float scale, spx_stream_t stream) {
     if (check_desc(d, "implicit_gemm_wgrad")) return 2;
     SPX_REQUIRE(d->dtype == SPX_F32 || d->dtype == SPX_F16 || d->dtype == SPX_BF16,
                 "implicit_gemm_wgrad: dtype %d not supported", d->dtype);
     SPX_REQUIRE(dfilters != nullptr, "implicit_gemm_wgrad: dfilters is NULL");
-    if (d->n_out == 0 || d->n_in == 0) {
-        SPX_CHECK_CUDA(cudaMemsetAsync(dfilters, 0, (size_t)d->kv * d->c_in * d->c_out * dtype_bytes(d->dtype),
-                                       (cudaStream_t)stream));
+    const int64_t dw_count = (int64_t)d->kv * d->c_in * d->c_out;
+    if (d->n_out == 0 || d->n_in == 0) {       // an empty shard still takes part in the exchange
+        SPX_CHECK_CUDA(cudaMemsetAsync(dfilters, 0, (size_t)dw_count * dtype_bytes(d->dtype), (cudaStream_t)stream));
+        if (pg) return peer_reduce_exchange(nullptr, 0, 0, dfilters, dw_count, dfilters, d->dtype, pg, scale, (cudaStream_t)stream);
         return 0;
     }
     SPX_REQUIRE(features && out_bp, "implicit_gemm_wgrad: NULL tensor");
     WgradArgs w = make_wgrad(d);
+    w.peers = pg; w.peer_scale = scale;
     w.x = features; w.dout = out_bp; w.dw = dfilters; w.workspace = workspace; w.workspace_bytes = workspace_bytes;
     bool exact_f32 = d->dtype == SPX_F32 && d->f32_mode == SPX_F32_EXACT;
     bool tc_ok = !force_simt() && !exact_f32 && tc_wgrad_supported(w);
@@ -125,7 +143,9 @@ extern "C" int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *featu
         return tc_wgrad(w, (cudaStream_t)stream);
     }
     set_family(1);
-    return simt_wgrad(w, (cudaStream_t)stream);
+    if (int rc = simt_wgrad(w, (cudaStream_t)stream)) return rc;
+    if (pg) return peer_reduce_exchange(nullptr, 0, 0, dfilters, dw_count, dfilters, d->dtype, pg, scale, (cudaStream_t)stream);
+    return 0;
 }
 
 extern "C" int spx_implicit_gemm_fwd_int8(const spx_gemm_desc *d, const int8_t *features, const int8_t *filters,

@@ -21,6 +21,7 @@
 // list scheduling without a run-time counter (round-robin over the unsorted tiles left the
 // slowest CTA ~15 us behind the median on the 100 k-voxel cloud).
 #include "gemm.cuh"
+#include "peer.cuh"
 #include <stdlib.h>
 
 namespace spx {
@@ -596,6 +597,8 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     fn<<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
     SPX_CHECK_LAUNCH("tc_wgrad_kernel");
     const int64_t total = pl.p.partial_stride;
+    if (a.peers)        // data-parallel: the reduction of the partials also sums over the ranks (peer.cu)
+        return peer_reduce_exchange(pl.p.partial, total, pl.chunks, nullptr, total, a.dw, a.dtype, a.peers, a.peer_scale, stream);
     unsigned nblk = (unsigned)div_up64(total, 128);
     if (a.dtype == SPX_F16)
         wgrad_reduce_kernel<__half><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__half *)a.dw);

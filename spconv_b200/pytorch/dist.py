@@ -9,10 +9,13 @@ single flat bucket rather than per-tensor collectives.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from .. import _cabi
 
 
 def shard_batch(indices: torch.Tensor, features: torch.Tensor, batch_size: int, rank: int,
@@ -93,3 +96,105 @@ def allreduce_gradients(module: torch.nn.Module, group: Optional[dist.ProcessGro
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+class PeerGroup:
+    """The exchange buffers of a data-parallel group, for the weight-gradient all-reduce fused into the
+    weight-gradient kernel (``csrc/peer.cu``; ``include/spconv_b200.h`` ``spx_peer_group``).
+
+        peers = PeerGroup()                       # after init_process_group; one process per GPU of ONE node
+        ops.set_peer_group(peers)                 # every dW now comes back summed (mean) over the ranks
+        ...
+        loss.backward()                           # no all-reduce call, no gradient bucket
+
+    Every rank allocates one buffer (``2 x world x capacity`` bytes), exports a CUDA IPC handle, and maps
+    the others' (NVLink peer access).  ``capacity_bytes`` bounds the largest weight tensor, counted as
+    fp32 (default 8 MB = 27 x 256 x 256 and some).  ``scale`` multiplies the sum (``1 / world`` = mean, the
+    DDP convention).  Raises if peer mapping is not possible -- callers that can live without the fused
+    path catch that and fall back to :class:`GradBucket`."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, capacity_bytes: int = 8 << 20,
+                 average: bool = True, timeout_ms: int = 20000, device: Optional[torch.device] = None):
+        lib = _cabi.load()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        assert self.world <= _cabi.SPX_MAX_PEERS, f"at most {_cabi.SPX_MAX_PEERS} ranks"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.scale = 1.0 / self.world if average else 1.0
+        self._lib = lib
+        self._mapped: List[int] = []
+        with torch.cuda.device(self.device):
+            own = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            _cabi.check(lib.spx_peer_buffer_create(capacity_bytes, self.world, ctypes.byref(own), handle),
+                        "peer_buffer_create")
+            self._own = own.value
+            handles: List[Optional[bytes]] = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            else:
+                handles[0] = bytes(handle)
+            g = _cabi.PeerGroup()
+            g.world, g.rank, g.timeout_ms, g.capacity_bytes = self.world, self.rank, timeout_ms, capacity_bytes
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    g.buffers[r] = self._own
+                    continue
+                mapped = ctypes.c_void_p()
+                raw = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _cabi.check(lib.spx_peer_buffer_open(raw, ctypes.byref(mapped)), f"peer_buffer_open(rank {r})")
+                self._mapped.append(mapped.value)
+                g.buffers[r] = mapped.value
+            self.group = g
+            torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)               # nobody pushes before every buffer is mapped and zeroed
+
+    @classmethod
+    def local_ring(cls, world: int, capacity_bytes: int = 8 << 20, average: bool = True,
+                   timeout_ms: int = 5000) -> List["PeerGroup"]:
+        """``world`` groups whose buffers all live on the CURRENT device of this process: the exchange
+        protocol between "ranks" that are streams of one GPU.  Test fixture (single-GPU boxes)."""
+        lib = _cabi.load()
+        bufs = []
+        for _ in range(world):
+            own = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            _cabi.check(lib.spx_peer_buffer_create(capacity_bytes, world, ctypes.byref(own), handle), "peer_buffer_create")
+            bufs.append(own.value)
+        out = []
+        for r in range(world):
+            pg = object.__new__(cls)
+            pg.world, pg.rank, pg.scale = world, r, (1.0 / world if average else 1.0)
+            pg.device = torch.device("cuda", torch.cuda.current_device())
+            pg._lib, pg._mapped, pg._own = lib, [], bufs[r]
+            g = _cabi.PeerGroup()
+            g.world, g.rank, g.timeout_ms, g.capacity_bytes = world, r, timeout_ms, capacity_bytes
+            for q in range(world):
+                g.buffers[q] = bufs[q]
+            pg.group = g
+            out.append(pg)
+        torch.cuda.synchronize()
+        return out
+
+    def error(self) -> int:
+        """Sticky error word of this rank's buffer: 1 = a peer did not arrive within the timeout (the
+        affected gradients are NaN).  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        e = ctypes.c_int(0)
+        _cabi.check(self._lib.spx_peer_error(ctypes.byref(self.group), ctypes.byref(e)), "peer_error")
+        return e.value
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free this rank's (all ranks: after a barrier / synchronize)."""
+        if getattr(self, "_lib", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for m in self._mapped:
+                self._lib.spx_peer_buffer_close(m)
+            self._mapped = []
+            if self._own:
+                self._lib.spx_peer_buffer_destroy(self._own)
+                self._own = None
+        self._lib = None

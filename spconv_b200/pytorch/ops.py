@@ -639,9 +639,15 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
 
     def run_wgrad():
         with timer.record("implicit_gemm_wgrad", _stream()):
-            _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
-                                                    _ptr(dfilters), ws.data_ptr(), ws.numel(),
-                                                    _stream()), "implicit_gemm_wgrad")
+            if _PEERS is not None:
+                # data-parallel: dW leaves the kernel already summed over the ranks (csrc/peer.cu)
+                _cabi.check(lib.spx_implicit_gemm_wgrad_allreduce(
+                    ctypes.byref(d_wg), _ptr(features), _ptr(out_bp), _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                    ctypes.byref(_PEERS.group), _PEERS.scale, _stream()), "implicit_gemm_wgrad_allreduce")
+            else:
+                _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
+                                                        _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                                                        _stream()), "implicit_gemm_wgrad")
 
     if _WGRAD_HOOK is not None and n_in and n_out:
         # Data-parallel overlap: weight gradient FIRST, then the hook (typically the all-reduce of dW) on
@@ -686,6 +692,30 @@ def set_wgrad_hook(fn) -> None:
     ``None`` removes the hook."""
     global _WGRAD_HOOK
     _WGRAD_HOOK = fn
+
+
+_PEERS = None
+
+
+def set_peer_group(peers) -> None:
+    """Data-parallel mode: with a :class:`spconv_b200.pytorch.dist.PeerGroup` installed, every weight
+    gradient computed by :func:`implicit_gemm_backward` / :func:`indice_conv_backward` is returned
+    already summed (x ``peers.scale``) over the ranks -- the exchange is the tail of the
+    weight-gradient kernel (NVLink peer stores, ``csrc/peer.cu``), there is no separate all-reduce.
+    Every rank must run the same sequence of layers.  ``None`` switches it off."""
+    global _PEERS
+    _PEERS = peers
+
+
+def peer_allreduce_(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum (x scale) of a small tensor over the installed peer group (bias gradients, weight
+    gradients of layers that do not run the implicit-GEMM kernels); no-op without a group."""
+    if _PEERS is None or t.numel() == 0:
+        return t
+    assert t.is_contiguous(), "peer_allreduce_: contiguous tensor"
+    _cabi.check(_lib().spx_peer_allreduce(ctypes.byref(_PEERS.group), t.data_ptr(), t.numel(), _DTYPE_CODE[t.dtype],
+                                          _PEERS.scale, _stream()), "peer_allreduce")
+    return t
 
 
 # ---------------------------------------------------------------------------- ConvAlgo.Native
@@ -771,9 +801,14 @@ def indice_conv_backward(features: torch.Tensor, filters: torch.Tensor, out_bp: 
     d_wg = _desc(features.dtype, kv, c_in, c_out, n_in, n_out, t_fwd, m_fwd, None, tiles=tiles_fwd)
     ws = _bytes(lib.spx_implicit_gemm_wgrad_workspace_size(ctypes.byref(d_wg)), features.device)
     with timer.record("indice_conv_wgrad", _stream()):
-        _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
-                                                _ptr(dfilters), ws.data_ptr(), ws.numel(),
-                                                _stream()), "implicit_gemm_wgrad(native)")
+        if _PEERS is not None:
+            _cabi.check(lib.spx_implicit_gemm_wgrad_allreduce(
+                ctypes.byref(d_wg), _ptr(features), _ptr(out_bp), _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                ctypes.byref(_PEERS.group), _PEERS.scale, _stream()), "implicit_gemm_wgrad_allreduce(native)")
+        else:
+            _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
+                                                    _ptr(dfilters), ws.data_ptr(), ws.numel(),
+                                                    _stream()), "implicit_gemm_wgrad(native)")
     return din, dfilters
 
 
