@@ -82,7 +82,8 @@ def parse_args():
     ap.add_argument("--graph", type=int, default=1, help="replay the device-resident step from CUDA graphs")
     ap.add_argument("--pipeline", type=int, default=2,
                     help="software-pipeline the graph replay: 1 = rulebook of cloud i+1 beside the GEMMs of cloud i "
-                         "(streams joined every step), 2 = rulebooks two clouds ahead on two side streams, 0 = serial")
+                         "(streams joined every step), 2 = rulebooks two clouds ahead on two side streams, 0 = serial; "
+                         "3 = 2 + the eager encoder prefetches its whole rulebook chain from a worker thread")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
@@ -454,8 +455,11 @@ class EncoderWorkload(Workload):
         # every layer's rulebook (the strided ones included) is built ahead of the step that uses it,
         # on the side stream, by a worker thread: the output-count read-backs of the three regular
         # convs then wait for rulebook kernels only, never for the GEMM queue of the training stream.
-        self.pipelined = bool(ctx.args.pipeline)
-        self.prefetcher = ctx.spconv.RulebookPrefetcher(self.layers, stream=ctx.side, background=self.pipelined)
+        # (--pipeline 3 only: measured SLOWER than the plain eager step, 2.01 vs 1.69 ms -- the worker thread's
+        # Python competes with the training thread for the GIL; profiles/README.md session f)
+        self.pipelined = int(ctx.args.pipeline) >= 3
+        self.prefetcher = ctx.spconv.RulebookPrefetcher(self.layers if self.pipelined else [self.layers[0]], stream=ctx.side,
+                                                        background=self.pipelined)
         self.staged = {}
         self.layer_stats = None
 

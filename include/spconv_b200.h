@@ -269,7 +269,7 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
 typedef struct spx_peer_group {
     int world, rank;
     int timeout_ms;                 /* a peer that does not arrive in time: NaN result + spx_peer_error (0 = 20 s) */
-    int reserved;
+    int colocated;                  /* ranks of this group that share ONE device (tests); 0 or 1 = one rank per GPU */
     uint64_t capacity_bytes;        /* largest exchanged tensor, as fp32 (what spx_peer_buffer_create got) */
     void *buffers[SPX_MAX_PEERS];   /* exchange buffer of every rank */
 } spx_peer_group;

@@ -47,7 +47,7 @@ SPX_MAX_PEERS = 16
 class PeerGroup(Structure):
     """``spx_peer_group``: the exchange buffers of a data-parallel group as mapped in this process."""
     _fields_ = [
-        ("world", c_int), ("rank", c_int), ("timeout_ms", c_int), ("reserved", c_int),
+        ("world", c_int), ("rank", c_int), ("timeout_ms", c_int), ("colocated", c_int),
         ("capacity_bytes", c_uint64),
         ("buffers", c_void_p * SPX_MAX_PEERS),
     ]

@@ -180,10 +180,13 @@ peer_reduce_exchange_kernel(const float *__restrict__ partial, int64_t stride, i
     }
 }
 
-static int px_grid(int64_t total) {
-    // co-resident by construction: 2 CTAs of 256 threads per SM at most (an SM holds 8)
+static int px_grid(int64_t total, int colocated) {
+    // co-resident by construction: 2 CTAs of 256 threads per SM at most (an SM holds 8).  When several ranks
+    // share this device (single-GPU protocol tests only) a waiting exchange CTA could keep another rank's
+    // weight-gradient CTA (57 k registers) off its SM, so all of them together stay on a quarter of the SMs.
     int64_t items = div_up64(total, 128);
-    int64_t cap = (int64_t)sm_count() * 2;
+    int64_t cap = colocated > 1 ? sm_count() / (4 * colocated) : (int64_t)sm_count() * 2;
+    if (cap < 1) cap = 1;
     return (int)(items < cap ? items : cap);
 }
 
@@ -204,7 +207,7 @@ int peer_reduce_exchange(const float *partial, int64_t stride, int chunks, const
     memset(&pp, 0, sizeof(pp));
     for (int r = 0; r < pg->world; ++r) pp.buf[r] = (char *)pg->buffers[r];
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
-    const int grid = px_grid(total);
+    const int grid = px_grid(total, pg->colocated);
     const unsigned long long timeout_ns = (unsigned long long)(pg->timeout_ms > 0 ? pg->timeout_ms : 20000) * 1000000ull;
     if (total == 0) return 0;
 #define PX_LAUNCH(T)                                                                                                   \

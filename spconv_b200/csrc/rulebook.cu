@@ -17,6 +17,8 @@
 
 namespace spx {
 size_t radix_argsort_workspace_bytes(int64_t n);
+int radix_argsort_pair(uint32_t *mask0, int32_t *argsort0, int64_t n0, uint32_t *mask1, int32_t *argsort1, int64_t n1,
+                       int key_bits, void *ws0, size_t ws0_bytes, void *ws1, size_t ws1_bytes, cudaStream_t stream);
 int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
                   cudaStream_t stream);
 }
@@ -354,7 +356,7 @@ __global__ void conv_insert_k3_kernel(Table table, Geom g, const int32_t *__rest
 template <typename Table>
 __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restrict__ indices, int64_t N, int64_t M,
                                      int32_t *__restrict__ pair_fwd, int32_t *__restrict__ pair_bwd,
-                                     uint32_t *__restrict__ mask_bwd) {
+                                     uint32_t *__restrict__ mask_bwd, uint32_t *__restrict__ mask_fwd_or) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
@@ -378,7 +380,11 @@ __global__ void conv_pairs_k3_kernel(Table table, Geom g, const int32_t *__restr
                     if (table.find_slot(key, v) >= 0) out = v;
                 }
                 pair_bwd[(int64_t)k * N + i] = out;
-                if (out >= 0) { pair_fwd[(int64_t)k * M + out] = (int32_t)i; mword |= 1u << k; }
+                if (out >= 0) {
+                    pair_fwd[(int64_t)k * M + out] = (int32_t)i;
+                    mword |= 1u << k;
+                    if (mask_fwd_or) atomicOr(&mask_fwd_or[out], 1u << k);   // zeroed by conv_assign_rank_kernel
+                }
             }
         }
     }
@@ -483,12 +489,87 @@ conv_insert_append_kernel(Table table, Geom g, const int32_t *__restrict__ indic
     if (created) slot_list[base_s + warp_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (uint32_t)slot;
 }
 
-// first-touch payload of every created slot (final only after ALL inserts: atomicMin keeps lowering it)
+// ---- ranking the outputs by first touch WITHOUT a sort.  Every output's final payload p = k*N + i
+// (the smallest (offset, input) pair that produces it) is distinct, so the rank of an output is the
+// number of outputs with a smaller payload = the number of set bits below p in a bitmap over
+// [0, kv*N).  mark: one atomicOr per output (+ a count per 1024-bit tile); scan: exclusive prefix over
+// the tile counts (one block); assign: tile prefix + popcount of at most 32 words.  Replaces the
+// radix sort of the payloads (1 + 2 x 3 launches at 22 key bits) by one single-block kernel.
+constexpr int RANK_TILE_WORDS = 32;              // bitmap words per counted tile (1024 payloads)
+static size_t rank_scratch_bytes(int64_t kvn, int64_t *ntiles = nullptr) {
+    const int64_t words = div_up64(kvn > 0 ? kvn : 1, 32), tiles = div_up64(words, RANK_TILE_WORDS);
+    if (ntiles) *ntiles = tiles;
+    return align_up((size_t)(tiles * RANK_TILE_WORDS + tiles + 1) * 4, 256);
+}
+
 template <typename Table>
-__global__ void conv_fetch_payload_kernel(Table table, const uint32_t *__restrict__ slot_list, int64_t M,
-                                          uint32_t *__restrict__ payload) {
+__global__ void conv_mark_kernel(Table table, const uint32_t *__restrict__ slot_list, int64_t M,
+                                 uint32_t *__restrict__ bitmap, int *__restrict__ tile_cnt) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j < M) payload[j] = (uint32_t)table.value_at(slot_list[j]);
+    if (j >= M) return;
+    const uint32_t p = (uint32_t)table.value_at(slot_list[j]);   // final: all inserts finished in an earlier kernel
+    atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+    atomicAdd(&tile_cnt[p >> 10], 1);
+}
+
+constexpr int RANK_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(RANK_SCAN_THREADS) rank_scan_kernel(int *__restrict__ tile_cnt, int64_t tiles) {
+    __shared__ int warp_sums[RANK_SCAN_THREADS / 32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t t0 = 0; t0 < tiles; t0 += RANK_SCAN_THREADS) {
+        const int64_t t = t0 + threadIdx.x;
+        const int v = t < tiles ? tile_cnt[t] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            warp_sums[lane] = wi - w;              // exclusive warp bases
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (t < tiles) tile_cnt[t] = carry + warp_sums[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == RANK_SCAN_THREADS - 1) carry_s = carry + warp_sums[warp] + incl;
+        __syncthreads();
+    }
+}
+
+// created slot j -> rank r of its payload: write r into the slot, decode the key into out_inds[r]
+template <typename Table>
+__global__ void conv_assign_rank_kernel(Table table, Geom g, const uint32_t *__restrict__ slot_list, int64_t M,
+                                        const uint32_t *__restrict__ bitmap, const int *__restrict__ tile_prefix,
+                                        int32_t *__restrict__ out_inds, uint32_t *__restrict__ mask_zero) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const uint32_t s = slot_list[j];
+    int64_t key; int32_t val;
+    table.occupied(s, key, val);
+    const uint32_t p = (uint32_t)val, word = p >> 5, first = word & ~(uint32_t)(RANK_TILE_WORDS - 1);
+    int r = __ldg(tile_prefix + (p >> 10)) + __popc(__ldg(bitmap + word) & ((1u << (p & 31)) - 1u));
+    for (uint32_t wd = first; wd < word; ++wd) r += __popc(__ldg(bitmap + wd));
+    table.set_value(s, r);
+    if (mask_zero) mask_zero[r] = 0u;              // the pairs kernel ORs the forward masks into it
+    int32_t *dst = out_inds + (int64_t)r * (g.ndim + 1);
+    for (int a = g.ndim - 1; a >= 0; --a) {
+        dst[a + 1] = (int32_t)(key % g.out_dims[a]);
+        key /= g.out_dims[a];
+    }
+    dst[0] = (int32_t)key;
 }
 
 // compact occupied slots -> (first-touch payload, slot); order irrelevant (sorted next).
@@ -733,11 +814,27 @@ __global__ void gather_rows_kernel(const uint32_t *__restrict__ src, const int32
 // ------------------------------------------------------------------ tile-blocked gather table
 // one block per 128-row tile; see include/spconv_b200.h (spx_build_tile_table)
 constexpr int TT_SPLIT = 4;                     // threads per tile row: offsets k = q, q + 4, ...
+// (blockIdx.y picks one of up to two jobs: a regular conv builds its forward and backward tables in one launch)
+struct TtJob {
+    const int32_t *pair; int64_t pair_stride;
+    const int32_t *argsort; const uint32_t *mask;
+    int64_t rows;
+    int32_t *table; uint32_t *tile_mask;
+};
+struct TtJobs { TtJob j[2]; };
+
 __global__ void __launch_bounds__(128 * TT_SPLIT)
-build_tile_table_kernel(const int32_t *__restrict__ pair, int64_t pair_stride, int kv,
-                        const int32_t *__restrict__ argsort, const uint32_t *__restrict__ mask, int64_t rows,
-                        int words, int32_t *__restrict__ table, uint32_t *__restrict__ tile_mask) {
+build_tile_table_kernel(const TtJobs jobs, int kv, int words) {
+    const TtJob &J = jobs.j[blockIdx.y];
     const int64_t t = blockIdx.x;
+    if (t * 128 >= J.rows) return;
+    const int32_t *__restrict__ pair = J.pair;
+    const int64_t pair_stride = J.pair_stride;
+    const int32_t *__restrict__ argsort = J.argsort;
+    const uint32_t *__restrict__ mask = J.mask;
+    const int64_t rows = J.rows;
+    int32_t *__restrict__ table = J.table;
+    uint32_t *__restrict__ tile_mask = J.tile_mask;
     const int r = threadIdx.x & 127;
     const int q = threadIdx.x >> 7;             // warp-uniform
     const int64_t j = t * 128 + r;
@@ -811,9 +908,15 @@ build_tile_table_rows_kernel(const int32_t *__restrict__ row_table, int kv, cons
 // One block; chunks of 1024 tiles are ranked with warp match_any + per-warp bucket counts.
 constexpr int TO_THREADS = 1024;
 constexpr int TO_BUCKETS = 130;                 // stage counts 0..128 (+1 spare)
+struct ToJob { const uint32_t *tile_mask; int tiles; int32_t *rec; int32_t *state; };
+struct ToJobs { ToJob j[2]; };
 __global__ void __launch_bounds__(TO_THREADS)
-tile_order_kernel(const uint32_t *__restrict__ tile_mask, int tiles, int words, int32_t *__restrict__ rec,
-                  int32_t *__restrict__ state) {
+tile_order_kernel(const ToJobs jobs, int words) {
+    const ToJob &J = jobs.j[blockIdx.x];
+    const uint32_t *__restrict__ tile_mask = J.tile_mask;
+    const int tiles = J.tiles;
+    int32_t *__restrict__ rec = J.rec;
+    int32_t *__restrict__ state = J.state;
     __shared__ int bucket_base[TO_BUCKETS];
     __shared__ int wcnt[TO_THREADS / 32][TO_BUCKETS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -948,6 +1051,7 @@ extern "C" size_t spx_rulebook_workspace_size(const spx_conv_geometry *g, int64_
         total += 5 * align_up((size_t)max_out * 4, 256);          // payload, slot (in + out), order
         total += align_up(sort_pairs_temp_bytes(max_out), 256);
         total += align_up(radix_argsort_workspace_bytes(max_out), 256);
+        total += align_up(rank_scratch_bytes((int64_t)gg.kv * num_in), 256);
         total += 256;                                             // counter
     }
     return total + 1024;
@@ -1015,9 +1119,12 @@ struct ConvWs {
     void *sort_tmp; size_t sort_tmp_bytes;
     int32_t *order;                    // argsort of the payloads (default path)
     void *radix_ws; size_t radix_ws_bytes;
+    uint32_t *rank_bitmap; int *rank_tiles;     // first-touch ranking (default path): bitmap over kv*N + tile counts
+    size_t rank_bytes; int64_t rank_ntiles;
     int *counter;
     RbLayout L;
 };
+
 // which table capacity stage 1 ended up with (the optimistic size, or the full one after an overflow);
 // stage 2 is called right after stage 1 on the same thread with the same workspace
 struct ConvStage1Record { const void *ws; uint32_t capacity; bool legacy; };
@@ -1046,6 +1153,9 @@ int carve_conv_ws(const spx_conv_geometry *g, const Geom &gg, int64_t N, void *w
     w.order = ws.take<int32_t>(max_out);
     w.radix_ws_bytes = radix_argsort_workspace_bytes(max_out);
     w.radix_ws = ws.take<char>(w.radix_ws_bytes);
+    w.rank_bytes = rank_scratch_bytes((int64_t)gg.kv * N, &w.rank_ntiles);
+    w.rank_bitmap = (uint32_t *)ws.take<char>(w.rank_bytes);
+    w.rank_tiles = (int *)(w.rank_bitmap + w.rank_ntiles * RANK_TILE_WORDS);
     w.counter = ws.take<int>(64);
     SPX_REQUIRE(ws.ok(), "rulebook workspace too small: need %zu, have %zu", ws.off, bytes);
     return 0;
@@ -1078,6 +1188,7 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
         const int64_t max_out = spx_conv_max_out(g, N);
         int host_state[2] = {0, 0};
         uint32_t capacity = optimistic_capacity(max_out, w.L.capacity);
+        SPX_CHECK_CUDA(cudaMemsetAsync(w.rank_bitmap, 0, w.rank_bytes, stream));
         for (int attempt = 0; attempt < 2; ++attempt) {
             SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, (size_t)capacity * 8, stream));
             SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(int), stream));
@@ -1107,15 +1218,15 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
         const unsigned mblk = (unsigned)div_up64(m_host, 256);
         if (!w.L.i64) {
             Table32 t{(unsigned long long *)w.tbl, capacity - 1};
-            conv_fetch_payload_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.payload);
+            conv_mark_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles);
         } else {
             Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
-            conv_fetch_payload_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.payload);
+            conv_mark_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles);
         }
-        SPX_CHECK_LAUNCH("conv_fetch_payload_kernel");
-        int key_bits = 1;
-        while (key_bits < 32 && ((int64_t)1 << key_bits) < (int64_t)gg.kv * N) ++key_bits;
-        return radix_argsort(w.payload, w.order, m_host, key_bits, w.radix_ws, w.radix_ws_bytes, stream);
+        SPX_CHECK_LAUNCH("conv_mark_kernel");
+        rank_scan_kernel<<<1, RANK_SCAN_THREADS, 0, stream>>>(w.rank_tiles, w.rank_ntiles);
+        SPX_CHECK_LAUNCH("rank_scan_kernel");
+        return 0;
     }
     SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
     SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
@@ -1174,24 +1285,28 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
                 "conv_rulebook_stage2 must follow conv_rulebook_stage1 on the same thread with the same workspace");
     const bool legacy = g_stage1.legacy;
     const uint32_t capacity = g_stage1.capacity;
+    // 3x3x3, one mask word: the pairs kernel ORs the forward masks too (zeroed by the assign kernel)
+    uint32_t *mask_fwd_or = (k3 && !legacy && mask_fwd && words == 1) ? mask_fwd : nullptr;
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, capacity - 1};
-        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, legacy ? w.slot_sorted : w.slot, legacy ? nullptr : w.order, M, out_inds);
+        if (legacy) conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, nullptr, M, out_inds);
+        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd, mask_fwd_or);
         else if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table32, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     } else {
         Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
-        conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, legacy ? w.slot_sorted : w.slot, legacy ? nullptr : w.order, M, out_inds);
+        if (legacy) conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, nullptr, M, out_inds);
+        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
-        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd);
+        if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd, mask_fwd_or);
         else if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         else conv_pairs_kernel<Table64, false><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
         SPX_CHECK_LAUNCH("conv_pairs_kernel");
     }
-    if (mask_fwd) {
+    if (mask_fwd && !mask_fwd_or) {
         table_mask_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(pair_fwd, M, gg.kv, words, mask_fwd);
         SPX_CHECK_LAUNCH("table_mask_kernel");
     }
@@ -1335,15 +1450,47 @@ extern "C" int spx_build_tile_table(const int32_t *pair, int64_t pair_stride, in
             row_table, kv, argsort, mask, rows, table, tile_mask);
         SPX_CHECK_LAUNCH("build_tile_table_rows_kernel");
     } else {
-        build_tile_table_kernel<<<(unsigned)div_up64(rows, 128), 128 * TT_SPLIT, 0, stream>>>(
-            pair, pair_stride, kv, argsort, mask, rows, words, table, tile_mask);
+        TtJobs jobs;
+        memset(&jobs, 0, sizeof(jobs));
+        jobs.j[0] = TtJob{pair, pair_stride, argsort, mask, rows, table, tile_mask};
+        build_tile_table_kernel<<<dim3((unsigned)div_up64(rows, 128), 1), 128 * TT_SPLIT, 0, stream>>>(jobs, kv, words);
         SPX_CHECK_LAUNCH("build_tile_table_kernel");
     }
     const int64_t tiles = div_up64(rows, 128);
     SPX_REQUIRE(tiles < 2147483647ll, "build_tile_table: too many tiles");
     SPX_REQUIRE(((uintptr_t)table & 15u) == 0, "build_tile_table: table must be 16-byte aligned");
     int32_t *rec = table + tt_blocks_elems(tiles, kv);
-    tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(tile_mask, (int)tiles, words, rec, rec + tiles * TT_REC_INTS);
+    ToJobs oj;
+    memset(&oj, 0, sizeof(oj));
+    oj.j[0] = ToJob{tile_mask, (int)tiles, rec, rec + tiles * TT_REC_INTS};
+    tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(oj, words);
+    SPX_CHECK_LAUNCH("tile_order_kernel");
+    return 0;
+}
+
+// forward + backward tile tables of a regular conv in one launch each (gather kernel, schedule records)
+static int build_tile_tables_pair(int kv, const int32_t *pair0, const int32_t *argsort0, const uint32_t *mask0, int64_t rows0,
+                                  int32_t *table0, uint32_t *tmask0, const int32_t *pair1, const int32_t *argsort1,
+                                  const uint32_t *mask1, int64_t rows1, int32_t *table1, uint32_t *tmask1,
+                                  cudaStream_t stream) {
+    SPX_REQUIRE(kv >= 1 && kv <= 128, "build_tile_table: kernel volume %d not in [1,128]", kv);
+    const int words = (kv + 31) / 32;
+    const int64_t tiles0 = div_up64(rows0, 128), tiles1 = div_up64(rows1, 128);
+    SPX_REQUIRE(tiles0 < 2147483647ll && tiles1 < 2147483647ll, "build_tile_table: too many tiles");
+    SPX_REQUIRE((((uintptr_t)table0 | (uintptr_t)table1) & 15u) == 0, "build_tile_table: table must be 16-byte aligned");
+    TtJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.j[0] = TtJob{pair0, rows0, argsort0, mask0, rows0, table0, tmask0};
+    jobs.j[1] = TtJob{pair1, rows1, argsort1, mask1, rows1, table1, tmask1};
+    const int64_t tmax = tiles0 > tiles1 ? tiles0 : tiles1;
+    build_tile_table_kernel<<<dim3((unsigned)tmax, 2), 128 * TT_SPLIT, 0, stream>>>(jobs, kv, words);
+    SPX_CHECK_LAUNCH("build_tile_table_kernel");
+    int32_t *rec0 = table0 + tt_blocks_elems(tiles0, kv), *rec1 = table1 + tt_blocks_elems(tiles1, kv);
+    ToJobs oj;
+    memset(&oj, 0, sizeof(oj));
+    oj.j[0] = ToJob{tmask0, (int)tiles0, rec0, rec0 + tiles0 * TT_REC_INTS};
+    oj.j[1] = ToJob{tmask1, (int)tiles1, rec1, rec1 + tiles1 * TT_REC_INTS};
+    tile_order_kernel<<<2, TO_THREADS, 0, stream>>>(oj, words);
     SPX_CHECK_LAUNCH("tile_order_kernel");
     return 0;
 }
@@ -1394,7 +1541,7 @@ extern "C" size_t spx_conv_rulebook_all_workspace_size(const spx_conv_geometry *
     for (int a = 0; a < g->ndim; ++a) kv *= g->ksize[a];
     const int64_t max_rows = spx_conv_max_out(g, N) > N ? spx_conv_max_out(g, N) : N;
     return align_up(spx_rulebook_workspace_size(g, N, 0, 0), 256) +
-           align_up(spx_mask_argsort_workspace_size(max_rows, (kv + 31) / 32), 256) + 256;
+           2 * align_up(spx_mask_argsort_workspace_size(max_rows, (kv + 31) / 32), 256) + 256;   // two sorts side by side
 }
 
 // stage 2 + both mask argsorts + both tile tables (argsort_bwd / table_bwd may be NULL: inference)
@@ -1415,6 +1562,21 @@ extern "C" int spx_conv_rulebook_stage2_all(const spx_conv_geometry *g, const in
     void *sort_ws = (char *)workspace + align_up(rb, 256);
     const size_t sort_bytes = workspace_bytes - align_up(rb, 256);
     if (int rc = spx_conv_rulebook_stage2(g, indices, N, M, out_inds, pair_fwd, pair_bwd, mask_fwd, mask_bwd, workspace, rb, stream)) return rc;
+    if (words == 1 && do_sort && argsort_bwd && !(runtime_cfg().debug & 2048)) {
+        // both mask sorts, then both tile tables, two jobs per launch (debug bit 2048: one after the other)
+        const size_t half = (sort_bytes / 2) & ~(size_t)255;
+        const int key_bits = kv < 32 ? kv : 32;
+        if (int rc = radix_argsort_pair(mask_fwd, argsort_fwd, M, mask_bwd, argsort_bwd, N, key_bits, sort_ws, half,
+                                        (char *)sort_ws + half, half, (cudaStream_t)stream)) return rc;
+        if (table_fwd && table_bwd)
+            return build_tile_tables_pair(kv, pair_fwd, argsort_fwd, mask_fwd, M, table_fwd, tmask_fwd, pair_bwd, argsort_bwd,
+                                          mask_bwd, N, table_bwd, tmask_bwd, (cudaStream_t)stream);
+        if (table_fwd)
+            if (int rc = spx_build_tile_table(pair_fwd, M, kv, argsort_fwd, mask_fwd, M, nullptr, table_fwd, tmask_fwd, stream)) return rc;
+        if (table_bwd)
+            if (int rc = spx_build_tile_table(pair_bwd, N, kv, argsort_bwd, mask_bwd, N, nullptr, table_bwd, tmask_bwd, stream)) return rc;
+        return 0;
+    }
     if (int rc = spx_mask_argsort(mask_fwd, argsort_fwd, M, words, kv, do_sort, sort_ws, sort_bytes, stream)) return rc;
     if (table_fwd)
         if (int rc = spx_build_tile_table(pair_fwd, M, kv, argsort_fwd, mask_fwd, M, nullptr, table_fwd, tmask_fwd, stream)) return rc;

@@ -40,8 +40,26 @@ constexpr int RS_AGG_SLOTS = 1 << RS_AGG_BITS;     // shared-memory merge table,
 constexpr int RS_TILE_SHIFT = 10;
 static_assert((1 << RS_TILE_SHIFT) == RS_TILE, "tile shift");
 
+// One launch serves up to two independent sorts (blockIdx.y picks the job): a regular conv sorts its
+// forward masks (M outputs) and its backward masks (N inputs) -- at rulebook sizes every kernel here is
+// latency-bound, so two jobs in one launch cost about as much as one.
+struct RsJob {
+    const uint32_t *kin; const int32_t *vin;
+    int64_t n; int nblk;
+    int *counts; int *totals;
+    uint32_t *kout; int32_t *vout;
+    int *counts_next;
+};
+struct RsJobs { RsJob j[2]; };
+
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk, int *__restrict__ counts) {
+rs_hist_kernel(const RsJobs jobs, int shift) {
+    const RsJob &J = jobs.j[blockIdx.y];
+    if ((int)blockIdx.x >= J.nblk) return;
+    const uint32_t *__restrict__ keys = J.kin;
+    const int64_t n = J.n;
+    const int nblk = J.nblk;
+    int *__restrict__ counts = J.counts;
     __shared__ int hist[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) hist[i] = 0;
     __syncthreads();
@@ -58,7 +76,13 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int nblk
 
 // counts[d][b] -> exclusive prefix over b, totals[d] = sum_b; zeroes row d of the next pass's buffer
 __global__ void __launch_bounds__(RS_THREADS)
-rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals, int *__restrict__ clear_next) {
+rs_scan_kernel(const RsJobs jobs) {
+    const RsJob &J = jobs.j[blockIdx.y];
+    int *__restrict__ counts = J.counts;
+    const int nblk = J.nblk;
+    int *__restrict__ totals = J.totals;
+    int *__restrict__ clear_next = J.counts_next;
+    if (nblk == 0) return;
     const int d = blockIdx.x;
     if (clear_next)
         for (int b = threadIdx.x; b < nblk; b += RS_THREADS) clear_next[(int64_t)d * nblk + b] = 0;
@@ -92,9 +116,18 @@ rs_scan_kernel(int *__restrict__ counts, int nblk, int *__restrict__ totals, int
 // counts hold block prefixes (rs_scan_kernel); counts_next (may be null) receives the next pass's histogram
 template <bool IOTA_IN>
 __global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
-                  int nblk, const int *__restrict__ counts, const int *__restrict__ totals,
-                  uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out, int *__restrict__ counts_next) {
+rs_scatter_kernel(const RsJobs jobs, int shift) {
+    const RsJob &J = jobs.j[blockIdx.y];
+    if ((int)blockIdx.x >= J.nblk) return;
+    const uint32_t *__restrict__ keys_in = J.kin;
+    const int32_t *__restrict__ vals_in = J.vin;
+    const int64_t n = J.n;
+    const int nblk = J.nblk;
+    const int *__restrict__ counts = J.counts;
+    const int *__restrict__ totals = J.totals;
+    uint32_t *__restrict__ keys_out = J.kout;
+    int32_t *__restrict__ vals_out = J.vout;
+    int *__restrict__ counts_next = J.counts_next;
     __shared__ int digit_base[RS_BINS];             // global position of this block's first key of each digit
     __shared__ int warp_cnt[RS_WARPS][RS_BINS];     // running per-warp digit counts -> warp bases
     __shared__ int scan_tmp[RS_WARPS];
@@ -497,6 +530,9 @@ size_t radix_argsort_workspace_bytes(int64_t n) {
     return 4 * align_up((size_t)n * 4, 256) + (legacy > sweep ? legacy : sweep) + 1024;
 }
 
+int radix_argsort_pair(uint32_t *mask0, int32_t *argsort0, int64_t n0, uint32_t *mask1, int32_t *argsort1, int64_t n1,
+                       int key_bits, void *ws0, size_t ws0_bytes, void *ws1, size_t ws1_bytes, cudaStream_t stream);
+
 // keys: mask [n] (sorted in place on return), argsort [n] out.  Returns 0 / error code.
 int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, void *workspace, size_t workspace_bytes,
                   cudaStream_t stream) {
@@ -557,31 +593,77 @@ int radix_argsort(uint32_t *mask, int32_t *argsort, int64_t n, int key_bits, voi
         }
         return 0;
     }
-    int *counts_ab[2] = {ws.take<int>((size_t)RS_BINS * nblk), ws.take<int>((size_t)RS_BINS * nblk)};
-    int *totals = ws.take<int>(RS_BINS);
-    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, workspace_bytes);
-    rs_hist_kernel<<<nblk, RS_THREADS, 0, stream>>>(kin, n, 0, nblk, counts_ab[0]);
+    return radix_argsort_pair(mask, argsort, n, nullptr, nullptr, 0, key_bits, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+namespace {
+struct RsPlan {
+    uint32_t *keys_a, *keys_b; int32_t *vals_a, *vals_b;
+    int *counts_ab[2]; int *totals;
+    int nblk;
+};
+int rs_carve(int64_t n, void *workspace, size_t bytes, RsPlan &p) {
+    WorkspaceCarver ws(workspace, bytes);
+    p.keys_a = ws.take<uint32_t>(n); p.vals_a = ws.take<int32_t>(n);
+    p.keys_b = ws.take<uint32_t>(n); p.vals_b = ws.take<int32_t>(n);
+    p.nblk = (int)div_up64(n, RS_TILE);
+    p.counts_ab[0] = ws.take<int>((size_t)RS_BINS * p.nblk);
+    p.counts_ab[1] = ws.take<int>((size_t)RS_BINS * p.nblk);
+    p.totals = ws.take<int>(RS_BINS);
+    SPX_REQUIRE(ws.ok(), "argsort workspace too small: need %zu, have %zu", ws.off, bytes);
+    return 0;
+}
+}  // namespace
+
+// Two-kernel-per-pass LSD sort of one or two independent key arrays with the same key width (n1 == 0: one job).
+int radix_argsort_pair(uint32_t *mask0, int32_t *argsort0, int64_t n0, uint32_t *mask1, int32_t *argsort1, int64_t n1,
+                       int key_bits, void *ws0, size_t ws0_bytes, void *ws1, size_t ws1_bytes, cudaStream_t stream) {
+    if (n0 == 0 && n1 == 0) return 0;
+    if (n0 == 0) return radix_argsort_pair(mask1, argsort1, n1, nullptr, nullptr, 0, key_bits, ws1, ws1_bytes, nullptr, 0, stream);
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 32) key_bits = 32;
+    const int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    const int njobs = n1 > 0 ? 2 : 1;
+    RsPlan pl[2];
+    uint32_t *masks[2] = {mask0, mask1};
+    int32_t *argsorts[2] = {argsort0, argsort1};
+    const int64_t ns[2] = {n0, n1};
+    if (int rc = rs_carve(n0, ws0, ws0_bytes, pl[0])) return rc;
+    if (njobs == 2) if (int rc = rs_carve(n1, ws1, ws1_bytes, pl[1])) return rc;
+    RsJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    int max_nblk = 0;
+    for (int q = 0; q < njobs; ++q) {
+        jobs.j[q].kin = masks[q]; jobs.j[q].vin = nullptr; jobs.j[q].n = ns[q]; jobs.j[q].nblk = pl[q].nblk;
+        jobs.j[q].totals = pl[q].totals;
+        if (pl[q].nblk > max_nblk) max_nblk = pl[q].nblk;
+    }
+    const dim3 grid_tiles(max_nblk, njobs), grid_scan(RS_BINS, njobs);
+    for (int q = 0; q < njobs; ++q) jobs.j[q].counts = pl[q].counts_ab[0];
+    rs_hist_kernel<<<grid_tiles, RS_THREADS, 0, stream>>>(jobs, 0);
     SPX_CHECK_LAUNCH("rs_hist_kernel");
     for (int pass = 0; pass < passes; ++pass) {
         const bool last = pass == passes - 1;
-        uint32_t *kout = (pass & 1) ? keys_b : keys_a;
-        int32_t *vout = (pass & 1) ? vals_b : vals_a;
-        if (last && pass > 0) { kout = mask; vout = argsort; }      // never aliases kin (kin is a scratch buffer)
-        const int shift = pass * RS_BITS;
-        int *counts = counts_ab[pass & 1];
-        int *counts_next = last ? nullptr : counts_ab[(pass + 1) & 1];
-        rs_scan_kernel<<<RS_BINS, RS_THREADS, 0, stream>>>(counts, nblk, totals, counts_next);
+        for (int q = 0; q < njobs; ++q) {
+            RsJob &J = jobs.j[q];
+            J.kout = (pass & 1) ? pl[q].keys_b : pl[q].keys_a;
+            J.vout = (pass & 1) ? pl[q].vals_b : pl[q].vals_a;
+            if (last && pass > 0) { J.kout = masks[q]; J.vout = argsorts[q]; }   // never aliases kin (kin is a scratch buffer)
+            J.counts = pl[q].counts_ab[pass & 1];
+            J.counts_next = last ? nullptr : pl[q].counts_ab[(pass + 1) & 1];
+        }
+        rs_scan_kernel<<<grid_scan, RS_THREADS, 0, stream>>>(jobs);
         SPX_CHECK_LAUNCH("rs_scan_kernel");
-        if (pass == 0)
-            rs_scatter_kernel<true><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout, counts_next);
-        else
-            rs_scatter_kernel<false><<<nblk, RS_THREADS, 0, stream>>>(kin, vin, n, shift, nblk, counts, totals, kout, vout, counts_next);
+        if (pass == 0) rs_scatter_kernel<true><<<grid_tiles, RS_THREADS, 0, stream>>>(jobs, pass * RS_BITS);
+        else rs_scatter_kernel<false><<<grid_tiles, RS_THREADS, 0, stream>>>(jobs, pass * RS_BITS);
         SPX_CHECK_LAUNCH("rs_scatter_kernel");
-        kin = kout; vin = vout;
+        for (int q = 0; q < njobs; ++q) { jobs.j[q].kin = jobs.j[q].kout; jobs.j[q].vin = jobs.j[q].vout; }
     }
     if (passes == 1) {   // single pass wrote to scratch: copy back
-        SPX_CHECK_CUDA(cudaMemcpyAsync(mask, keys_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
-        SPX_CHECK_CUDA(cudaMemcpyAsync(argsort, vals_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        for (int q = 0; q < njobs; ++q) {
+            SPX_CHECK_CUDA(cudaMemcpyAsync(masks[q], pl[q].keys_a, (size_t)ns[q] * 4, cudaMemcpyDeviceToDevice, stream));
+            SPX_CHECK_CUDA(cudaMemcpyAsync(argsorts[q], pl[q].vals_a, (size_t)ns[q] * 4, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     return 0;
 }

@@ -169,7 +169,7 @@ class PeerGroup:
             pg.device = torch.device("cuda", torch.cuda.current_device())
             pg._lib, pg._mapped, pg._own = lib, [], bufs[r]
             g = _cabi.PeerGroup()
-            g.world, g.rank, g.timeout_ms, g.capacity_bytes = world, r, timeout_ms, capacity_bytes
+            g.world, g.rank, g.timeout_ms, g.capacity_bytes, g.colocated = world, r, timeout_ms, capacity_bytes, world
             for q in range(world):
                 g.buffers[q] = bufs[q]
             pg.group = g

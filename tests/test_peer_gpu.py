@@ -36,6 +36,11 @@ def _shard(cuda_dev, seed, C, K, subm, dt, pts=(1200, 900)):
     return x, dout, res
 
 
+def _weights(cuda_dev, seed, C, K, dt):
+    w = np.random.default_rng(seed).uniform(-0.5, 0.5, size=(K, 3, 3, 3, C)).astype(np.float32)
+    return torch.from_numpy(w).to(cuda_dev, dt)
+
+
 def _backward(x, w, dout, res, subm):
     from spconv_b200.pytorch import ops
     return ops.implicit_gemm_backward(x, w, dout, res[2], res[3], res[4], res[5], res[6], res[7], None, res[8], 128, subm)
@@ -56,7 +61,7 @@ def test_world_of_one_equals_the_plain_weight_gradient(cuda_dev, no_peers):
                                            (64, 64, True, torch.float16), (48, 24, True, torch.float16),
                                            (16, 16, True, torch.float32), (64, 64, True, torch.float16)]):
         x, dout, res = _shard(cuda_dev, 100 + it, C, K, subm, dt)
-        w = (torch.rand((K, 3, 3, 3, C), device=cuda_dev) - 0.5).to(dt)
+        w = _weights(cuda_dev, it, C, K, dt)
         ops.set_peer_group(None)
         din0, dw0 = _backward(x, w, dout, res, subm)
         ops.set_peer_group(pg)
@@ -76,7 +81,7 @@ def test_ranks_on_one_gpu_exchange_through_the_fused_kernel(world, cuda_dev, no_
     cases = [(64, 64, True, torch.float16), (64, 128, False, torch.bfloat16), (32, 32, True, torch.float16),
              (48, 24, True, torch.float16), (64, 64, True, torch.float16)]       # K=24: FMA kernel + standalone exchange
     for it, (C, K, subm, dt) in enumerate(cases * 2):                               # 10 exchanges: slots, epochs, sizes
-        w = (torch.rand((K, 3, 3, 3, C), device=cuda_dev) - 0.5).to(dt)
+        w = _weights(cuda_dev, it, C, K, dt)
         shards = [_shard(cuda_dev, 1000 + 10 * it + r, C, K, subm, dt, pts=(900 + 150 * r, 700)) for r in range(world)]
         ops.set_peer_group(None)
         local = [_backward(x, w, dout, res, subm)[1] for x, dout, res in shards]
@@ -106,9 +111,9 @@ def test_small_tensor_allreduce_in_place(cuda_dev, no_peers):
     world = 4
     ring = PeerGroup.local_ring(world, capacity_bytes=1 << 18, average=False)
     streams = [torch.cuda.Stream() for _ in range(world)]
-    g = torch.Generator(device=cuda_dev).manual_seed(3)
+    rng = np.random.default_rng(3)
     for n in (4, 3, 64, 1001, 40000, 64):
-        parts = [torch.randn(n, device=cuda_dev, generator=g) for _ in range(world)]
+        parts = [torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(cuda_dev) for _ in range(world)]
         want = parts[0].clone()
         for p in parts[1:]:
             want = want + p                                   # rank order, fp32: exact match expected

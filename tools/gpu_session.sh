@@ -8,7 +8,5 @@ echo "== session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.
 (timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -400) > $O/${TAG}_tests.log
 tail -6 $O/${TAG}_tests.log | cut -c1-300
 (timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
-for W in second_encoder6_fp16 second_encoder6_fp16_b8; do for P in 2 0; do
-(timeout 300 python bench.py --workload $W --pipeline $P --extras 0 --steps 10 > $O/${TAG}_bench_${W}_p$P.json 2>> $O/${TAG}_bench.err); python -c "import json; d=json.loads(open('$O/${TAG}_bench_${W}_p$P.json').read().strip().splitlines()[-1]); print('$W pipeline $P', round(d['value']/1e6,2), 'Mvox/s', round(d['ms_per_step'],4), 'ms; e2e', d['e2e'].get('ms_per_step'), d['e2e'].get('eager_variant'), d['e2e'].get('eager_prefetch_ms_per_step'), d['e2e'].get('eager_naive_ms_per_step'), 'launches', d['gpu_launches'])"
-done; done
+(timeout 200 python tools/ab_conv_rulebook.py > $O/${TAG}_ab_conv_rulebook.log 2>&1); cat $O/${TAG}_ab_conv_rulebook.log | tail -8
 echo "== done $(date -u +%H:%M:%S)"

@@ -33,8 +33,7 @@ def main():
                                                  st, [1] * 3, [1] * 3, [0] * 3, subm, False, is_train=True)
         x = torch.from_numpy(feats).to(dev, dt)
         dout = torch.from_numpy(rng.uniform(-0.2, 0.2, size=(res[0].shape[0], K)).astype(np.float32)).to(dev, dt)
-        g = torch.Generator(device=dev).manual_seed(it)
-        w = (torch.rand((K, 3, 3, 3, C), device=dev, generator=g) - 0.5).to(dt)   # replicated weights
+        w = torch.from_numpy(np.random.default_rng(it).uniform(-0.5, 0.5, size=(K, 3, 3, 3, C)).astype(np.float32)).to(dev, dt)  # replicated
         args = (x, w, dout, res[2], res[3], res[4], res[5], res[6], res[7], None, res[8], 128, subm)
         ops.set_peer_group(None)
         local = ops.implicit_gemm_backward(*args)[1].float()
