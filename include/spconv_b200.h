@@ -256,14 +256,17 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel weight-gradient exchange over NVLink peer memory.  The reference has no
  * distributed code: users wrap it in torch DDP, i.e. an NCCL all-reduce of dW after the backward
- * pass.  Here the all-reduce is the tail of the weight-gradient kernel itself (csrc/peer.cu): every
- * rank pushes its fp32 slice sums into every rank's exchange buffer and reduces the world's slices
- * locally, in rank order, so all replicas end with bit-identical gradients after one rounding.
+ * pass.  Here the SEND side is the tail of the weight-gradient kernel itself (csrc/peer.cu): every rank
+ * pushes its fp32 slice sums into every rank's exchange buffer; the RECEIVE side (finish) sums the
+ * world's slices locally, in rank order, so all replicas end with bit-identical gradients after one
+ * rounding.  Put independent work (the input gradient of the same layer) between push and finish and
+ * the NVLink latency is hidden.
  *
  * Set-up (once per process group; the host side passes the 64-byte handles around, e.g. with
  * torch.distributed.all_gather_object): every rank creates its buffer, opens the others', and fills
  * a spx_peer_group with the addresses AS MAPPED IN ITS OWN PROCESS (buffers[rank] = its own).
- * Calls on one group must be stream-ordered on each rank and issued in the same order on all ranks.
+ * Contract: on each rank, push and finish of one group alternate in stream order (one exchange in
+ * flight), and all ranks issue the same sequence of exchanges.
  */
 #define SPX_MAX_PEERS 16
 typedef struct spx_peer_group {
@@ -282,14 +285,20 @@ int spx_peer_buffer_destroy(void *buffer);
 /* sticky error word of this rank's buffer (1 = a peer timed out); synchronous copy */
 int spx_peer_error(const spx_peer_group *pg, int *error);
 
-/* dfilters = scale * sum over ranks of this rank's weight gradient (see spx_implicit_gemm_wgrad); one
- * rounding, identical bits on every rank.  Shapes the tcgen05 kernel does not tile fall back to the
- * FMA weight gradient followed by spx_peer_allreduce. */
+/* Weight gradient of this rank (see spx_implicit_gemm_wgrad), pushed to every rank of the group in fp32
+ * by the kernel that reduces the split-K partials.  dfilters is NOT valid afterwards (scratch for shapes
+ * the tcgen05 kernel does not tile): spx_peer_finish(pg, dfilters, kv*C*K, dtype, scale) writes it. */
+int spx_implicit_gemm_wgrad_push(const spx_gemm_desc *d, const void *features, const void *out_bp,
+                                 void *dfilters, void *workspace, size_t workspace_bytes,
+                                 const spx_peer_group *pg, spx_stream_t stream);
+/* push + finish back to back: dfilters = scale * sum over ranks */
 int spx_implicit_gemm_wgrad_allreduce(const spx_gemm_desc *d, const void *features, const void *out_bp,
                                       void *dfilters, void *workspace, size_t workspace_bytes,
                                       const spx_peer_group *pg, float scale, spx_stream_t stream);
-/* data = scale * sum over ranks of data, in place (bias gradients and other small tensors);
- * dtype SPX_F32 / SPX_F16 / SPX_BF16 */
+/* the same exchange for an existing small tensor (bias gradients ...): push sends `data` (dtype SPX_F32 /
+ * SPX_F16 / SPX_BF16), finish writes out = scale * sum over ranks (out may be data); allreduce = both */
+int spx_peer_push(const spx_peer_group *pg, const void *data, int64_t count, int dtype, spx_stream_t stream);
+int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t count, int dtype, float scale, spx_stream_t stream);
 int spx_peer_allreduce(const spx_peer_group *pg, void *data, int64_t count, int dtype, float scale,
                        spx_stream_t stream);
 

@@ -42,8 +42,7 @@ struct WgradArgs {
     const uint32_t *tile_mask; // [tiles][words] or NULL
     void *workspace;
     size_t workspace_bytes;
-    const spx_peer_group *peers;   // NULL, or: all-reduce dW over these ranks in the reduction tail
-    float peer_scale;
+    const spx_peer_group *peers;   // NULL, or: push this rank's fp32 dW to these ranks instead of writing dw
 };
 
 // Layout of the buffer spx_build_tile_table fills (int32 elements):

@@ -597,8 +597,9 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     fn<<<grid, WG_THREADS, pl.smem, stream>>>(pl.p);
     SPX_CHECK_LAUNCH("tc_wgrad_kernel");
     const int64_t total = pl.p.partial_stride;
-    if (a.peers)        // data-parallel: the reduction of the partials also sums over the ranks (peer.cu)
-        return peer_reduce_exchange(pl.p.partial, total, pl.chunks, nullptr, total, a.dw, a.dtype, a.peers, a.peer_scale, stream);
+    if (a.peers)        // data-parallel: the reduction of the partials IS the send side of the exchange (peer.cu); the
+                        // caller finishes it (peer_finish writes dW) after the work it wants to overlap
+        return peer_push(pl.p.partial, total, pl.chunks, nullptr, total, a.dtype, a.peers, stream);
     unsigned nblk = (unsigned)div_up64(total, 128);
     if (a.dtype == SPX_F16)
         wgrad_reduce_kernel<__half><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__half *)a.dw);

@@ -4,10 +4,11 @@
 
 namespace spx {
 
-// Sum `total` fp32 values over the ranks of `pg` and write them (x scale, rounded once) to `dst` in `dtype`.
-// The local contribution is either the sum of `chunks` split-K partials (`partial` != NULL, row stride
-// `stride` floats) or the tensor `src` (may alias `dst`).
-int peer_reduce_exchange(const float *partial, int64_t stride, int chunks, const void *src, int64_t total, void *dst,
-                         int dtype, const spx_peer_group *pg, float scale, cudaStream_t stream);
+// push: this rank's `total` fp32 values -- the sum of `chunks` split-K partials (`partial` != NULL, row stride
+// `stride` floats) or the tensor `src` of `dtype` -- go to every rank's exchange buffer.  Never waits.
+int peer_push(const float *partial, int64_t stride, int chunks, const void *src, int64_t total, int dtype,
+              const spx_peer_group *pg, cudaStream_t stream);
+// finish: wait for every rank's push, dst = scale * sum over ranks (rank order, one rounding to `dtype`).
+int peer_finish(void *dst, int64_t total, int dtype, const spx_peer_group *pg, float scale, cudaStream_t stream);
 
 }  // namespace spx

@@ -502,26 +502,41 @@ static size_t rank_scratch_bytes(int64_t kvn, int64_t *ntiles = nullptr) {
     return align_up((size_t)(tiles * RANK_TILE_WORDS + tiles + 1) * 4, 256);
 }
 
-template <typename Table>
-__global__ void conv_mark_kernel(Table table, const uint32_t *__restrict__ slot_list, int64_t M,
-                                 uint32_t *__restrict__ bitmap, int *__restrict__ tile_cnt) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= M) return;
-    const uint32_t p = (uint32_t)table.value_at(slot_list[j]);   // final: all inserts finished in an earlier kernel
-    atomicOr(&bitmap[p >> 5], 1u << (p & 31));
-    atomicAdd(&tile_cnt[p >> 10], 1);
+// one launch clears everything stage 1 needs: hash table (0xFF), 64-bit-key value array (0x7F), ranking scratch and counters (0)
+__global__ void conv_clear_kernel(uint4 *__restrict__ table, int64_t table_vec, uint4 *__restrict__ tvals, int64_t tvals_vec,
+                                  uint4 *__restrict__ zero, int64_t zero_vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u), sf = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu),
+                zz = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < table_vec; i += stride) table[i] = ff;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tvals_vec; i += stride) tvals[i] = sf;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < zero_vec; i += stride) zero[i] = zz;
 }
 
-constexpr int RANK_SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(RANK_SCAN_THREADS) rank_scan_kernel(int *__restrict__ tile_cnt, int64_t tiles) {
-    __shared__ int warp_sums[RANK_SCAN_THREADS / 32];
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+constexpr int MARK_THREADS = 256;
+// mark every output's final payload; the LAST block to finish turns the tile counts into an exclusive prefix
+template <typename Table>
+__global__ void __launch_bounds__(MARK_THREADS)
+conv_mark_kernel(Table table, const uint32_t *__restrict__ slot_list, int64_t M, uint32_t *__restrict__ bitmap,
+                 int *__restrict__ tile_cnt, int64_t tiles, int *__restrict__ done) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < M) {
+        const uint32_t p = (uint32_t)table.value_at(slot_list[j]);   // final: all inserts finished in an earlier kernel
+        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+        atomicAdd(&tile_cnt[p >> 10], 1);
+    }
+    __shared__ int warp_sums[MARK_THREADS / 32];
+    __shared__ int carry_s, last_s;
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) { last_s = atomicAdd(done, 1) == (int)gridDim.x - 1; carry_s = 0; }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t t0 = 0; t0 < tiles; t0 += RANK_SCAN_THREADS) {
+    for (int64_t t0 = 0; t0 < tiles; t0 += MARK_THREADS) {
         const int64_t t = t0 + threadIdx.x;
-        const int v = t < tiles ? tile_cnt[t] : 0;
+        const int v = t < tiles ? __ldcg(tile_cnt + t) : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -530,21 +545,12 @@ __global__ void __launch_bounds__(RANK_SCAN_THREADS) rank_scan_kernel(int *__res
         }
         if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            const int w = warp_sums[lane];
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += up;
-            }
-            warp_sums[lane] = wi - w;              // exclusive warp bases
-        }
-        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warp_sums[w];
         const int carry = carry_s;
-        if (t < tiles) tile_cnt[t] = carry + warp_sums[warp] + incl - v;
+        if (t < tiles) tile_cnt[t] = carry + wbase + incl - v;
         __syncthreads();
-        if (threadIdx.x == RANK_SCAN_THREADS - 1) carry_s = carry + warp_sums[warp] + incl;
+        if (threadIdx.x == MARK_THREADS - 1) carry_s = carry + wbase + incl;
         __syncthreads();
     }
 }
@@ -553,9 +559,12 @@ __global__ void __launch_bounds__(RANK_SCAN_THREADS) rank_scan_kernel(int *__res
 template <typename Table>
 __global__ void conv_assign_rank_kernel(Table table, Geom g, const uint32_t *__restrict__ slot_list, int64_t M,
                                         const uint32_t *__restrict__ bitmap, const int *__restrict__ tile_prefix,
-                                        int32_t *__restrict__ out_inds, uint32_t *__restrict__ mask_zero) {
+                                        int32_t *__restrict__ out_inds, uint32_t *__restrict__ mask_zero,
+                                        int32_t *__restrict__ pair_fill, int kv) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= M) return;
+    if (pair_fill)                                  // column j of the forward table: -1 until the pairs kernel fills it
+        for (int k = 0; k < kv; ++k) pair_fill[(int64_t)k * M + j] = -1;
     const uint32_t s = slot_list[j];
     int64_t key; int32_t val;
     table.occupied(s, key, val);
@@ -1188,17 +1197,20 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
         const int64_t max_out = spx_conv_max_out(g, N);
         int host_state[2] = {0, 0};
         uint32_t capacity = optimistic_capacity(max_out, w.L.capacity);
-        SPX_CHECK_CUDA(cudaMemsetAsync(w.rank_bitmap, 0, w.rank_bytes, stream));
         for (int attempt = 0; attempt < 2; ++attempt) {
-            SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, (size_t)capacity * 8, stream));
-            SPX_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(int), stream));
+            // ranking scratch and counters are contiguous (carve_conv_ws): one region of zeros
+            const int64_t zero_vec = (int64_t)(((char *)(w.counter + 64) - (char *)w.rank_bitmap) / 16);
+            conv_clear_kernel<<<sm_count() * 4, 256, 0, stream>>>((uint4 *)w.tbl, (int64_t)capacity / 2,
+                                                                  w.L.i64 ? (uint4 *)w.tvals : nullptr,
+                                                                  w.L.i64 ? (int64_t)capacity / 4 : 0,
+                                                                  (uint4 *)w.rank_bitmap, zero_vec);
+            SPX_CHECK_LAUNCH("conv_clear_kernel");
             if (!w.L.i64) {
                 Table32 t{(unsigned long long *)w.tbl, capacity - 1};
                 if (k3) conv_insert_k3_append_kernel<<<(unsigned)div_up64(N, APPEND_THREADS), APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
                 else if (fast3) conv_insert_append_kernel<Table32, true><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
                 else conv_insert_append_kernel<Table32, false><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
             } else {
-                SPX_CHECK_CUDA(cudaMemsetAsync(w.tvals, 0x7F, (size_t)capacity * 4, stream));
                 Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
                 if (k3) conv_insert_k3_append_kernel<<<(unsigned)div_up64(N, APPEND_THREADS), APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
                 else if (fast3) conv_insert_append_kernel<Table64, true><<<grid, APPEND_THREADS, 0, stream>>>(t, gg, indices, N, w.slot, w.counter);
@@ -1215,17 +1227,15 @@ extern "C" int spx_conv_rulebook_stage1(const spx_conv_geometry *g, const int32_
         const int m_host = host_state[0];
         *num_out_host = m_host;
         if (m_host == 0) return 0;
-        const unsigned mblk = (unsigned)div_up64(m_host, 256);
+        const unsigned mblk = (unsigned)div_up64(m_host, MARK_THREADS);
         if (!w.L.i64) {
             Table32 t{(unsigned long long *)w.tbl, capacity - 1};
-            conv_mark_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles);
+            conv_mark_kernel<<<mblk, MARK_THREADS, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles, w.rank_ntiles, w.counter + 2);
         } else {
             Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
-            conv_mark_kernel<<<mblk, 256, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles);
+            conv_mark_kernel<<<mblk, MARK_THREADS, 0, stream>>>(t, w.slot, m_host, w.rank_bitmap, w.rank_tiles, w.rank_ntiles, w.counter + 2);
         }
         SPX_CHECK_LAUNCH("conv_mark_kernel");
-        rank_scan_kernel<<<1, RANK_SCAN_THREADS, 0, stream>>>(w.rank_tiles, w.rank_ntiles);
-        SPX_CHECK_LAUNCH("rank_scan_kernel");
         return 0;
     }
     SPX_CHECK_CUDA(cudaMemsetAsync(w.tbl, 0xFF, w.L.table_bytes, stream));
@@ -1280,17 +1290,17 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
     dim3 grid((unsigned)div_up64(N, T), gg.kv);
     const bool fast3 = gg.ndim == 3 && !gg.transposed;
     const bool k3 = fast3 && gg.ksize[0] == 3 && gg.ksize[1] == 3 && gg.ksize[2] == 3;
-    SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));
     SPX_REQUIRE(g_stage1.ws == workspace && g_stage1.capacity != 0,
                 "conv_rulebook_stage2 must follow conv_rulebook_stage1 on the same thread with the same workspace");
     const bool legacy = g_stage1.legacy;
+    if (legacy) SPX_CHECK_CUDA(cudaMemsetAsync(pair_fwd, 0xFF, (size_t)gg.kv * M * 4, stream));   // default: the assign kernel fills it
     const uint32_t capacity = g_stage1.capacity;
     // 3x3x3, one mask word: the pairs kernel ORs the forward masks too (zeroed by the assign kernel)
     uint32_t *mask_fwd_or = (k3 && !legacy && mask_fwd && words == 1) ? mask_fwd : nullptr;
     if (!w.L.i64) {
         Table32 t{(unsigned long long *)w.tbl, capacity - 1};
         if (legacy) conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, nullptr, M, out_inds);
-        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or);
+        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or, pair_fwd, gg.kv);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
         if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd, mask_fwd_or);
         else if (fast3) conv_pairs_kernel<Table32, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);
@@ -1299,7 +1309,7 @@ extern "C" int spx_conv_rulebook_stage2(const spx_conv_geometry *g, const int32_
     } else {
         Table64 t{(long long *)w.tbl, w.tvals, capacity - 1};
         if (legacy) conv_assign_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot_sorted, nullptr, M, out_inds);
-        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or);
+        else conv_assign_rank_kernel<<<(unsigned)div_up64(M, 256), 256, 0, stream>>>(t, gg, w.slot, M, w.rank_bitmap, w.rank_tiles, out_inds, mask_fwd_or, pair_fwd, gg.kv);
         SPX_CHECK_LAUNCH("conv_assign_kernel");
         if (k3) conv_pairs_k3_kernel<<<(unsigned)div_up64(N, T), T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd, mask_bwd, mask_fwd_or);
         else if (fast3) conv_pairs_kernel<Table64, true><<<grid, T, 0, stream>>>(t, gg, indices, N, M, pair_fwd, pair_bwd);

@@ -640,15 +640,37 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
     def run_wgrad():
         with timer.record("implicit_gemm_wgrad", _stream()):
             if _PEERS is not None:
-                # data-parallel: dW leaves the kernel already summed over the ranks (csrc/peer.cu)
-                _cabi.check(lib.spx_implicit_gemm_wgrad_allreduce(
+                # data-parallel: the kernel that reduces the split-K partials pushes this rank's fp32 dW into every
+                # rank's exchange buffer (csrc/peer.cu); finish_exchange() below writes dfilters
+                _cabi.check(lib.spx_implicit_gemm_wgrad_push(
                     ctypes.byref(d_wg), _ptr(features), _ptr(out_bp), _ptr(dfilters), ws.data_ptr(), ws.numel(),
-                    ctypes.byref(_PEERS.group), _PEERS.scale, _stream()), "implicit_gemm_wgrad_allreduce")
+                    ctypes.byref(_PEERS.group), _stream()), "implicit_gemm_wgrad_push")
             else:
                 _cabi.check(lib.spx_implicit_gemm_wgrad(ctypes.byref(d_wg), _ptr(features), _ptr(out_bp),
                                                         _ptr(dfilters), ws.data_ptr(), ws.numel(),
                                                         _stream()), "implicit_gemm_wgrad")
 
+    def finish_exchange():
+        with timer.record("implicit_gemm_wgrad_exchange", _stream()):
+            _cabi.check(lib.spx_peer_finish(ctypes.byref(_PEERS.group), _ptr(dfilters), dfilters.numel(),
+                                            _DTYPE_CODE[dfilters.dtype], _PEERS.scale, _stream()), "peer_finish")
+
+    if _PEERS is not None:
+        # push first, the input gradient hides the NVLink latency, then the local rank-order sum
+        if timer.enable or not (n_in and n_out) or not torch._C._cuda_isCurrentStreamCapturing():
+            run_wgrad()
+            run_dgrad()
+            finish_exchange()
+            return din, dfilters
+        main = torch.cuda.current_stream()
+        side = _side_stream(features.device)
+        side.wait_stream(main)
+        run_wgrad()
+        with torch.cuda.stream(side):
+            run_dgrad()
+        main.wait_stream(side)
+        finish_exchange()
+        return din, dfilters
     if _WGRAD_HOOK is not None and n_in and n_out:
         # Data-parallel overlap: weight gradient FIRST, then the hook (typically the all-reduce of dW) on
         # a forked stream while the input gradient -- which the hook does not need -- runs on this one.
