@@ -398,7 +398,8 @@ int64_t spx_launch_count(int reset);
  *   tc_ctas:      0 keep, 1 or 2 resident CTAs per SM for the forward / dgrad kernel;
  *   debug_bits:   A/B and ablation mask (bits 1..32: ablations of the tcgen05 kernels, results are wrong by
  *                 construction; 64 / 512: alternative sorts; 128: legacy regular-conv rulebook; 256: fp32+TF32
- *                 input gradient on the FMA kernel instead of tcgen05; 1024: weight-gradient pass split);
+ *                 input gradient on the FMA kernel instead of tcgen05, 4096: the same for the weight gradient;
+ *                 1024: weight-gradient pass split; 2048: regular-conv mask sorts / tile tables one job per launch);
  *   trace_buf:    NULL or a DEVICE buffer of at least 8*2048 int64 that receives clock stamps.
  */
 int spx_debug_configure(int force_family, int tc_ctas, int debug_bits, void *trace_buf,

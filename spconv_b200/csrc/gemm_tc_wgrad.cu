@@ -111,7 +111,16 @@ __device__ __forceinline__ uint32_t pick_word(const uint32_t (&m)[4], int w) {
 }
 
 // CPA = 16-byte chunks per x-atom row (span_x / 16), CPD = 16-byte chunks per dout row (db / 16)
-template <int CPA, int CPD>
+// 16-byte-chunk address swizzle of an MN-major operand row: SWIZZLE_{32,64,128}B for 16-bit operands; 32-bit
+// (tf32) MN-major operands use SWIZZLE_128B_BASE32B = CuTe Swizzle<2,5,2>: 32-byte units XORed with the row
+// inside its 4-row atom (the pattern TMA's 128B_ATOM_32B mode writes for the tf32 input-gradient filter box)
+template <bool TF32>
+__device__ __forceinline__ uint32_t wg_swizzle(uint32_t off, uint32_t span) {
+    if constexpr (TF32) return off ^ (((off >> 7) & 3u) << 5);
+    else return swizzle_offset(off, span);
+}
+
+template <int CPA, int CPD, bool TF32 = false>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgParams p) {
     constexpr int LG_CPA = CPA == 2 ? 1 : (CPA == 4 ? 2 : 3);
@@ -205,7 +214,7 @@ tc_wgrad_kernel(const WgParams p) {
         uint32_t dst_off[ITERS];
 #pragma unroll
         for (int itc = 0; itc < ITERS; ++itc)
-            dst_off[itc] = swizzle_offset(((uint32_t)(pw * ROWS_PW + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
+            dst_off[itc] = wg_swizzle<TF32>(((uint32_t)(pw * ROWS_PW + r0 + itc * RPI) << LG_SPAN_X) + chb, SPAN_X);
         const int lg_apo = p.apo == 1 ? 0 : (p.apo == 2 ? 1 : 2);
         // per-lane constants of the dout gather: chunk chd of rows rd0 + itc*RPI_D of this warp's rows
         const int rd0 = lane >> LG_CPD;
@@ -216,7 +225,7 @@ tc_wgrad_kernel(const WgParams p) {
         for (int itc = 0; itc < ITERS_D; ++itc) {
             const uint32_t row_in_tile = (uint32_t)(pw * ROWS_PW + rd0 + itc * RPI_D);
             dstd_off[itc] = (chd >> LG_SPAN_D) * (uint32_t)(WG_TILE * SPAN_D) +
-                            swizzle_offset((row_in_tile << LG_SPAN_D) + (chd & (uint32_t)(SPAN_D - 1)), SPAN_D);
+                            wg_swizzle<TF32>((row_in_tile << LG_SPAN_D) + (chd & (uint32_t)(SPAN_D - 1)), SPAN_D);
         }
         // index-block ring (filled by the feeder warp): slot / use count advance with the tiles
         const int nring = p.idx_bufs;
@@ -352,8 +361,11 @@ tc_wgrad_kernel(const WgParams p) {
         if (wg_rec_index(0, chunk, chunks) < num_tiles)
             wg_load_rec(p.sched_rec, wg_rec_index(0, chunk, chunks), tile_unused, tm);
         // both operands are MN-major: LBO = distance between 128-row atoms, SBO = 8 rows
-        const uint64_t a_hi = smem_desc_hi((uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
-        const uint64_t b_hi = smem_desc_hi((uint32_t)(WG_TILE * SPAN_D), 8u * SPAN_D, SPAN_D);
+        // (tf32: 4-row atoms of the SWIZZLE_128B_BASE32B layout, descriptor layout code 1 -- as in gemm_tc.cu)
+        const uint64_t a_hi = TF32 ? smem_desc_hi_layout((uint32_t)(WG_TILE * p.span_x), 4u * p.span_x, 1ull)
+                                   : smem_desc_hi((uint32_t)(WG_TILE * p.span_x), 8u * p.span_x, p.span_x);
+        const uint64_t b_hi = TF32 ? smem_desc_hi_layout((uint32_t)(WG_TILE * SPAN_D), 4u * SPAN_D, 1ull)
+                                   : smem_desc_hi((uint32_t)(WG_TILE * SPAN_D), 8u * SPAN_D, SPAN_D);
         const uint32_t a_step16 = (uint32_t)(p.rows_per_kstep * p.span_x) >> 4;
         const uint32_t b_step16 = (uint32_t)(p.rows_per_kstep * SPAN_D) >> 4;
         for (int64_t step = 0; wg_rec_index(step, chunk, chunks) < num_tiles; ++step) {
@@ -379,7 +391,7 @@ tc_wgrad_kernel(const WgParams p) {
                         for (int j = 0; j < p.ksteps; ++j) {
                             const uint64_t a_desc = a_hi | (uint64_t)((a16 + (uint32_t)j * a_step16) & 0x3FFFu);
                             const uint64_t b_desc = b_hi | (uint64_t)((b16 + (uint32_t)j * b_step16) & 0x3FFFu);
-                            umma_ss_elect<KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, acc_flag);
+                            umma_ss_elect<TF32 ? KIND_TF32 : KIND_F16>(d_tmem, a_desc, b_desc, p.idesc, acc_flag);
                             acc_flag = 1u;
                         }
                         tc_commit_elect(&empty_a[stage]);
@@ -504,10 +516,14 @@ static bool wg_span_ok(int bytes) { return bytes == 32 || bytes == 64 || (bytes 
 struct WgPlan { WgParams p; int passes, chunks; size_t smem; };
 
 static bool make_plan(const WgradArgs &a, WgPlan &pl) {
-    if (a.dtype != SPX_F16 && a.dtype != SPX_BF16) return false;     // tf32 MN-major needs SW128_32B atoms
+    if (a.dtype != SPX_F16 && a.dtype != SPX_BF16 && a.dtype != SPX_F32) return false;
     if (!a.tile_table || !a.tile_mask) return false;                 // built by spx_build_tile_table
-    const int e = 2;
+    const bool tf32 = a.dtype == SPX_F32;       // fp32 reaches here only in TF32 mode (api_gemm.cu)
+    const int e = tf32 ? 4 : 2;
     if (a.c_in % 16 || a.c_out % 16 || a.c_in > 256 || a.c_out > 256) return false;
+    // tf32: whole 128-byte atoms of 32 channels on both operands, dout rows of at most 512 bytes;
+    // spx_debug_configure bit 4096 sends it back to the FMA kernel (A/B)
+    if (tf32 && (a.c_in % 32 || a.c_out % 32 || a.c_out > 128 || (runtime_cfg().debug & 4096))) return false;
     if (!wg_span_ok(a.c_in * e) || !wg_span_ok(a.c_out * e)) return false;
     WgParams &p = pl.p;
     memset(&p, 0, sizeof(p));
@@ -524,7 +540,7 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     p.n = a.c_out;
     p.rows_per_kstep = 32 / e;
     p.ksteps = WG_TILE / p.rows_per_kstep;
-    const int ab_fmt = a.dtype == SPX_F16 ? 0 : 1;
+    const int ab_fmt = tf32 ? 2 : (a.dtype == SPX_F16 ? 0 : 1);
     p.idesc = make_idesc(1, ab_fmt, ab_fmt, 1, 1, 128, a.c_out);
     const int atoms_total = a.kv * p.apo;
     p.groups_total = (atoms_total + p.apg - 1) / p.apg;
@@ -538,7 +554,9 @@ static bool make_plan(const WgradArgs &a, WgPlan &pl) {
     p.a_stage_bytes = p.apg * WG_TILE * p.span_x;
     p.b_buf_bytes = WG_TILE * p.db;
     p.idx_bytes = (int)align_up((size_t)(a.kv + 1) * 512, 1024);
-    int avail = WG_SMEM_BUDGET - 2 * p.b_buf_bytes - 2 * p.idx_bytes;
+    // tf32 stages are twice as large (64 KB per group of four 32-channel atoms): two of them only fit without the
+    // head-room the 16-bit plans keep for a deeper index ring
+    int avail = (tf32 ? WG_SMEM_MAX - 2048 : WG_SMEM_BUDGET) - 2 * p.b_buf_bytes - 2 * p.idx_bytes;
     if (avail < 2 * p.a_stage_bytes) return false;
     p.stages = avail / p.a_stage_bytes;
     if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
@@ -585,11 +603,17 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
     const int cpa = pl.p.span_x >> 4, cpd = pl.p.db >> 4;
     using KernelFn = void (*)(const WgParams);
     KernelFn fn = nullptr;
+    if (a.dtype == SPX_F32) {
+        if (cpa == 8 && cpd == 8) fn = tc_wgrad_kernel<8, 8, true>;
+        if (cpa == 8 && cpd == 16) fn = tc_wgrad_kernel<8, 16, true>;
+        if (cpa == 8 && cpd == 32) fn = tc_wgrad_kernel<8, 32, true>;
+    } else {
 #define WG_PICK(A, D) if (cpa == A && cpd == D) fn = tc_wgrad_kernel<A, D>;
 #define WG_PICK_ROW(A) WG_PICK(A, 2) WG_PICK(A, 4) WG_PICK(A, 8) WG_PICK(A, 16) WG_PICK(A, 32)
-    WG_PICK_ROW(2) WG_PICK_ROW(4) WG_PICK_ROW(8)
+        WG_PICK_ROW(2) WG_PICK_ROW(4) WG_PICK_ROW(8)
 #undef WG_PICK_ROW
 #undef WG_PICK
+    }
     SPX_REQUIRE(fn != nullptr, "tc_wgrad: no kernel instance for this channel layout");
     if (!func_configured((const void *)fn, current_device()))      // per-device attribute
         SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -601,7 +625,9 @@ int tc_wgrad(const WgradArgs &a, cudaStream_t stream) {
                         // caller finishes it (peer_finish writes dW) after the work it wants to overlap
         return peer_push(pl.p.partial, total, pl.chunks, nullptr, total, a.dtype, a.peers, stream);
     unsigned nblk = (unsigned)div_up64(total, 128);
-    if (a.dtype == SPX_F16)
+    if (a.dtype == SPX_F32)
+        wgrad_reduce_kernel<float><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (float *)a.dw);
+    else if (a.dtype == SPX_F16)
         wgrad_reduce_kernel<__half><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__half *)a.dw);
     else
         wgrad_reduce_kernel<__nv_bfloat16><<<nblk, RED_WARPS * 32, 0, stream>>>(pl.p.partial, total, pl.chunks, total, (__nv_bfloat16 *)a.dw);

@@ -410,17 +410,18 @@ def test_int8_forward_at_config5_size(oracle, cuda_dev):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (diff.max(), (diff > 0).mean())
 
 
-def test_tf32_input_gradient_on_tensor_cores(oracle, cuda_dev, monkeypatch):
-    """fp32 + SPCONV_ALLOW_TF32: the input gradient runs on tcgen05 (kind::tf32, filter consumed as an MN-major
-    SWIZZLE_128B_BASE32B operand) and matches the fp32 oracle to tf32 accuracy; spx_debug_configure bit 256
-    routes it back to the FMA kernel."""
+def test_tf32_gradients_on_tensor_cores(oracle, cuda_dev, monkeypatch):
+    """fp32 + SPCONV_ALLOW_TF32: input gradient (kind::tf32, filter consumed as an MN-major SWIZZLE_128B_BASE32B operand
+    written by TMA) and weight gradient (both operands MN-major tf32, gathered by cp.async into the same layout) run
+    on tcgen05 and match the fp32 oracle to tf32 accuracy; spx_debug_configure bits 256 / 4096 route them back to
+    the FMA kernels."""
     from spconv_b200 import _cabi
     from spconv_b200.core import ConvAlgo
     from spconv_b200.pytorch import ops
     monkeypatch.setattr(ops, "SPCONV_ALLOW_TF32", True)
     lib = _cabi.load()
     try:
-        for C, K, subm in ((32, 64, True), (64, 64, True), (64, 32, False)):
+        for C, K, subm in ((32, 64, True), (64, 64, True), (64, 32, False), (32, 32, True)):
             s = _setup(oracle, cuda_dev, "f32", C, K, subm, stride=1 if subm else 2)
             inds = torch.from_numpy(s["inds"]).to(cuda_dev)
             res = ops.get_indice_pairs_implicit_gemm(inds, s["bs"], s["shape"], ConvAlgo.MaskImplicitGemm, s["ks"], s["st"],
@@ -432,23 +433,23 @@ def test_tf32_input_gradient_on_tensor_cores(oracle, cuda_dev, monkeypatch):
             dout = rng.uniform(-1, 1, size=(m, K)).astype(np.float32)
             args = (x, w, torch.from_numpy(dout).to(cuda_dev), res[2], res[3], res[4], res[5], res[6], res[7], None, res[8],
                     128, subm)
-            _cabi.check(lib.spx_debug_configure(-1, 0, 0, None, 0), "debug_configure")
-            din, dw = ops.implicit_gemm_backward(*args)
             ref_din, ref_dw = oracle.indice_conv_backward(s["feats"], s["w"], dout, s["pairs"], s["num"], False, subm)
-            assert rel_l2(din.cpu().numpy(), ref_din) < 2e-3, describe_mismatch(din.cpu().numpy(), ref_din, f"tf32 din C{C}K{K}")
-            assert rel_l2(dw.cpu().numpy(), ref_dw) < 2e-3
-            # which kernel served it: with the tensor-core family forced, the eager backward (input gradient first)
-            # gets past the input gradient and stops at the fp32 weight gradient, which has no tcgen05 kernel ...
+            # every kernel forced onto tcgen05: a shape it does not serve would raise
             _cabi.check(lib.spx_debug_configure(2, 0, 0, None, 0), "debug_configure")
-            with pytest.raises(RuntimeError, match="tcgen05 wgrad"):
-                ops.implicit_gemm_backward(*args)
-            # ... and with bit 256 the input gradient itself is refused
+            din, dw = ops.implicit_gemm_backward(*args)
+            assert rel_l2(din.cpu().numpy(), ref_din) < 2e-3, describe_mismatch(din.cpu().numpy(), ref_din, f"tf32 din C{C}K{K}")
+            assert rel_l2(dw.cpu().numpy(), ref_dw) < 2e-3, describe_mismatch(dw.cpu().numpy(), ref_dw, f"tf32 dw C{C}K{K}")
+            # the off switches are honoured: with the family still forced, the refused kernel raises
             _cabi.check(lib.spx_debug_configure(2, 0, 256, None, 0), "debug_configure")
             with pytest.raises(RuntimeError, match="tcgen05 path does not support"):
                 ops.implicit_gemm_backward(*args)
+            _cabi.check(lib.spx_debug_configure(2, 0, 4096, None, 0), "debug_configure")
+            with pytest.raises(RuntimeError, match="tcgen05 wgrad"):
+                ops.implicit_gemm_backward(*args)
             # the FMA route gives the same answer to tf32 accuracy
-            _cabi.check(lib.spx_debug_configure(0, 0, 256, None, 0), "debug_configure")
-            din_fma, _ = ops.implicit_gemm_backward(*args)
+            _cabi.check(lib.spx_debug_configure(0, 0, 256 | 4096, None, 0), "debug_configure")
+            din_fma, dw_fma = ops.implicit_gemm_backward(*args)
             assert rel_l2(din.cpu().numpy(), din_fma.cpu().numpy()) < 2e-3
+            assert rel_l2(dw.cpu().numpy(), dw_fma.cpu().numpy()) < 2e-3
     finally:
         _cabi.check(lib.spx_debug_configure(0, 0, 0, None, 0), "debug_configure")

@@ -18,6 +18,7 @@ except Exception as e:
     print("$1 FAILED", e)
 PY
 }
+(timeout 300 python -m pytest tests/test_peer_gpu.py tests/test_conv_gpu.py -m gpu -q -k "peer or tf32 or ipc or ranks or world or tensor or missing" 2>&1 | tail -15) > $O/${TAG}_tests.log; tail -3 $O/${TAG}_tests.log | cut -c1-300
 (timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/peer_check.py > $O/${TAG}_peer_check.log 2>&1); grep -v Warning $O/${TAG}_peer_check.log | tail -4 | cut -c1-400
 run bench ""
 run bench_nccl "--allreduce nccl"
