@@ -256,11 +256,12 @@ int spx_implicit_gemm_wgrad(const spx_gemm_desc *d, const void *features, const 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel weight-gradient exchange over NVLink peer memory.  The reference has no
  * distributed code: users wrap it in torch DDP, i.e. an NCCL all-reduce of dW after the backward
- * pass.  Here the SEND side is the tail of the weight-gradient kernel itself (csrc/peer.cu): every rank
- * pushes its fp32 slice sums into every rank's exchange buffer; the RECEIVE side (finish) sums the
- * world's slices locally, in rank order, so all replicas end with bit-identical gradients after one
- * rounding.  Put independent work (the input gradient of the same layer) between push and finish and
- * the NVLink latency is hidden.
+ * pass.  Here the SEND side is the tail of the weight-gradient kernel itself (csrc/peer.cu): the kernel
+ * that reduces the split-K partials writes this rank's fp32 slice sums into its own exchange buffer and
+ * its last CTA publishes the epoch to every rank (one system fence, `world` flag stores over NVLink).
+ * The RECEIVE side (finish) reads every rank's slices through the peer mapping and sums them in rank
+ * order, so all replicas end with bit-identical gradients after one rounding.  Put independent work (the
+ * input gradient of the same layer) between push and finish and the NVLink latency is hidden.
  *
  * Set-up (once per process group; the host side passes the 64-byte handles around, e.g. with
  * torch.distributed.all_gather_object): every rank creates its buffer, opens the others', and fills
@@ -285,8 +286,8 @@ int spx_peer_buffer_destroy(void *buffer);
 /* sticky error word of this rank's buffer (1 = a peer timed out); synchronous copy */
 int spx_peer_error(const spx_peer_group *pg, int *error);
 
-/* Weight gradient of this rank (see spx_implicit_gemm_wgrad), pushed to every rank of the group in fp32
- * by the kernel that reduces the split-K partials.  dfilters is NOT valid afterwards (scratch for shapes
+/* Weight gradient of this rank (see spx_implicit_gemm_wgrad), published to the group in fp32 by the kernel
+ * that reduces the split-K partials.  dfilters is NOT valid afterwards (scratch for shapes
  * the tcgen05 kernel does not tile): spx_peer_finish(pg, dfilters, kv*C*K, dtype, scale) writes it. */
 int spx_implicit_gemm_wgrad_push(const spx_gemm_desc *d, const void *features, const void *out_bp,
                                  void *dfilters, void *workspace, size_t workspace_bytes,

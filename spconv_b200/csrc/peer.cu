@@ -3,30 +3,36 @@
 // The only tensor that crosses GPUs on this path is dW (the reference itself has no
 // distributed code).  dW is small (27*C*K values: 0.4 MB fp32 at C = K = 64), so the exchange is
 // latency-bound and a library all-reduce costs more in launches and protocol than in bytes.  Here the
-// send side is the tail of the weight-gradient reduction itself and the receive side is a local sum:
+// send side is the tail of the weight-gradient reduction itself and the receive side is one small kernel:
 //
-//   push    (peer_push_kernel = the kernel that reduces the split-K partials of tc_wgrad_kernel, or reads
-//           an existing gradient): every CTA sums its 128-value slice in fp32 and stores it into EVERY
-//           rank's exchange buffer [slot][source rank][element] with plain 16-byte stores through the
-//           peer mapping (fire-and-forget over NVLink), then one release-add per CTA on every rank's
-//           arrival counter for this source.  Never waits.
-//   finish  (peer_finish_kernel): waits until every source has fully arrived (acquire loads on its OWN
-//           counters), sums the world's slices from LOCAL memory in rank order -- the same order on every
-//           rank, so all replicas get bit-identical gradients -- scales, rounds once, writes dW, and
-//           advances the epoch in device memory (CUDA-graph capturable: no host argument changes).
+//   publish (peer_push_kernel = the kernel that reduces the split-K partials of tc_wgrad_kernel, or reads
+//           an existing gradient): every CTA sums its 128-value slice in fp32 and writes it to this rank's
+//           OWN exchange buffer [slot][element] -- local stores, gpu-scope fence, one local counter.  The
+//           LAST CTA out makes the slices visible system-wide (one fence.sys per kernel) and stores the
+//           epoch into every rank's flag word for this source (world tiny release stores over NVLink).
+//           Never waits.
+//   finish  (peer_finish_kernel): waits until every source's flag shows this epoch (acquire loads on its
+//           OWN flags), reads the world's slices -- its own locally, the others through the peer mapping
+//           -- and sums them in rank order: the same order on every rank, so all replicas get bit-identical
+//           gradients; scales, rounds once, writes dW, advances the epoch in device memory (CUDA-graph
+//           capturable: no host argument changes between replays).
 //
-// The caller puts independent work between the two (the input-gradient kernel of the same layer): by
-// the time finish runs the slices have long arrived and it does not spin.  A first version did both
-// phases in ONE kernel: correct, but its ~20 us of NVLink latency sat on the critical path and the
-// spinning CTAs took issue slots from the input-gradient kernel beside it -- 0.169 vs 0.147 ms per
-// config-2 step at N = 2 against the NCCL hook (profiles/README.md, session n2b).
+// The caller puts independent work between the two (the input-gradient kernel of the same layer), so the
+// flags have long arrived when finish starts.  Two earlier versions, both correct, both measured at N = 2
+// against the NCCL hook (profiles/README.md, sessions n2b / n2c): (1) push + wait + sum in ONE kernel --
+// ~20 us of NVLink round trips on the critical path and 296 spinning CTAs beside the input-gradient
+// kernel: 0.169 vs 0.147 ms per config-2 step; (2) every CTA PUSHING its slice into every rank's buffer
+// with a fence.sys + remote arrival per CTA -- 864 system-scope fences made the reduction kernel 22 us
+// slower (86 vs 64 us weight gradient): 0.170 vs 0.146 ms.  Hence local writes, ONE system fence, and the
+// receiver pulling 0.44 MB per peer (a few us at NVLink 5 bandwidth).
 //
-// No grid-wide barrier, no host involvement.  push never waits, so ranks cannot deadlock each other;
+// No grid-wide barrier, no host involvement.  publish never waits, so ranks cannot deadlock each other;
 // a peer that never shows up trips the group's timeout in finish (error word + NaN result) instead of
-// hanging the GPU.  Two slots alternate by epoch: rank r's push of epoch e+2 is stream-ordered after
-// its finish of e+1, which needed every peer's push of e+1, which is stream-ordered after that peer's
-// finish of e -- so nobody is still reading slot e&1.  Hence the contract: on each rank push and finish
-// of one group alternate in stream order (one exchange in flight), same sequence on all ranks.
+// hanging the GPU.  Two slots alternate by epoch: rank r overwrites slot e&1 in its publish of epoch e+2,
+// which is stream-ordered after its finish of e+1, which needed every peer's flag of e+1, which that peer
+// stored after its own finish of e -- so nobody is still reading r's slot e&1.  Hence the contract: on
+// each rank publish and finish of one group alternate in stream order (one exchange in flight), same
+// sequence on all ranks.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "peer.cuh"
@@ -34,19 +40,26 @@
 namespace spx {
 
 // ---- exchange buffer layout (bytes from the base of each rank's buffer)
-//   [0, 64)      local state: epoch, finished CTAs of the running finish, arrivals expected so far, error
-//   [256, 320)   arrival counters, one per source rank (written by the peers)
-//   [4096, ...)  data [2 slots][world][capacity] fp32
-constexpr size_t PEER_COUNTERS = 256, PEER_DATA = 4096;
+//   [0, 64)      local state: epoch, finished CTAs of the running finish, CTAs done in the running publish, error
+//   [256, 320)   flags, one per source rank: last epoch (+1) that source has published (written by the peers)
+//   [4096, ...)  data [2 slots][capacity] fp32: this rank's own slices
+constexpr size_t PEER_FLAGS = 256, PEER_DATA = 4096;
 
-struct PeerState { unsigned epoch, finished, expected, error; };
+struct PeerState { unsigned epoch, finished, done, error; };
 
-__device__ __forceinline__ void red_release_sys_add(unsigned *addr, unsigned v) {
-    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_sys(unsigned *addr, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *addr) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+// system-scope load of a slice that another GPU wrote: must not be served from a stale cached line (the two
+// slots are rewritten every other epoch)
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float *addr) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -67,8 +80,9 @@ __global__ void __launch_bounds__(PX_THREADS)
 peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, const T *__restrict__ src, int64_t total,
                  PeerPtrs peers, int world, int rank, int64_t capacity) {
     __shared__ float4 acc_s[PX_WARPS][32];
-    __shared__ unsigned s_slot;
-    if (threadIdx.x == 0) s_slot = reinterpret_cast<const PeerState *>(peers.buf[rank])->epoch & 1u;
+    __shared__ unsigned s_epoch;
+    PeerState *st = reinterpret_cast<PeerState *>(peers.buf[rank]);
+    if (threadIdx.x == 0) s_epoch = st->epoch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * 32 + lane) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -86,6 +100,7 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     }
     __syncthreads();
     if (warp != 0) return;
+    const unsigned epoch = s_epoch;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (partial) {
         t = acc_s[0][lane];
@@ -100,49 +115,52 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
         if (i + 2 < total) t.z = to_float<T>(src[i + 2]);
         if (i + 3 < total) t.w = to_float<T>(src[i + 3]);
     }
-    if (i < total) {                                       // the padded tail of the last float4 carries zeros
-        const int64_t off = (int64_t)s_slot * world * capacity + (int64_t)rank * capacity + i;
-        for (int p = 0; p < world; ++p) {
-            const int q = (rank + p) % world;              // start at home, spread the link load
-            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.buf[q] + PEER_DATA) + off) = t;
-        }
-    }
-    __threadfence_system();                                // my stores before my CTA's arrival
+    if (i < total)                                         // the padded tail of the last float4 carries zeros
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.buf[rank] + PEER_DATA) + (int64_t)(epoch & 1u) * capacity + i) = t;
+    __threadfence();
     __syncwarp();
-    if (lane < world) red_release_sys_add(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_COUNTERS) + rank, 1u);
+    unsigned last = 0;
+    if (lane == 0) last = atomicAdd(&st->done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    // every slice of this rank is in its buffer: one system-scope fence, then tell everybody
+    __threadfence_system();
+    if (lane == 0) st->done = 0;
+    if (lane < world) st_release_sys(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_FLAGS) + rank, epoch + 1u);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
 peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world, int rank, int64_t capacity, float scale,
-                   unsigned arrivals, unsigned long long timeout_ns) {
-    __shared__ unsigned s_epoch, s_expected;
+                   unsigned long long timeout_ns) {
+    __shared__ unsigned s_epoch;
     __shared__ int s_bad;
     char *mine = peers.buf[rank];
     PeerState *st = reinterpret_cast<PeerState *>(mine);
-    if (threadIdx.x == 0) { s_epoch = st->epoch; s_expected = st->expected; s_bad = 0; }
+    if (threadIdx.x == 0) { s_epoch = st->epoch; s_bad = 0; }
     __syncthreads();
-    const unsigned epoch = s_epoch, target = s_expected + arrivals;
+    const unsigned epoch = s_epoch, target = epoch + 1u;
     if (threadIdx.x < world) {
-        const unsigned *ctr = reinterpret_cast<const unsigned *>(mine + PEER_COUNTERS) + threadIdx.x;
+        const unsigned *flag = reinterpret_cast<const unsigned *>(mine + PEER_FLAGS) + threadIdx.x;
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
-        while ((int)(ld_acquire_sys(ctr) - target) < 0) {
+        while ((int)(ld_acquire_sys(flag) - target) < 0) {
             if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) { s_bad = 1; break; }
         }
     }
     __syncthreads();
     const bool bad = s_bad != 0;
     if (bad && threadIdx.x == 0) st->error = 1u;
-    const float *data = reinterpret_cast<const float *>(mine + PEER_DATA) + (int64_t)(epoch & 1u) * world * capacity;
+    const int64_t slot_off = (int64_t)(epoch & 1u) * capacity;
     const int64_t n4 = (total + 3) / 4;
     const float nan = __int_as_float(0x7fc00000);
     for (int64_t g = (int64_t)blockIdx.x * PX_THREADS + threadIdx.x; g < n4; g += (int64_t)gridDim.x * PX_THREADS) {
         const int64_t i = g * 4;
-        float4 t = __ldcg(reinterpret_cast<const float4 *>(data + i));
-        for (int r = 1; r < world; ++r) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(data + (int64_t)r * capacity + i));
-            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {                  // rank order: identical bits on every rank
+            const float4 v = ld_relaxed_sys_f4(reinterpret_cast<const float *>(peers.buf[r] + PEER_DATA) + slot_off + i);
+            if (r == 0) t = v;
+            else { t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
         }
         if (bad) t = make_float4(nan, nan, nan, nan);
         dst[i] = from_float<T>(t.x * scale);
@@ -150,13 +168,12 @@ peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world
         if (i + 2 < total) dst[i + 2] = from_float<T>(t.z * scale);
         if (i + 3 < total) dst[i + 3] = from_float<T>(t.w * scale);
     }
-    // ---- the last CTA out advances the epoch (push / finish of one group alternate in stream order)
+    // ---- the last CTA out advances the epoch (publish / finish of one group alternate in stream order)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {
             st->finished = 0;
-            st->expected = target;
             st->epoch = epoch + 1;
             __threadfence();
         }
@@ -211,8 +228,7 @@ int peer_finish(void *dst, int64_t total, int dtype, const spx_peer_group *pg, f
     const int64_t cap_ctas = pg->colocated > 1 ? (sm_count() / (4 * pg->colocated) > 0 ? sm_count() / (4 * pg->colocated) : 1) : sm_count();
     const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap_ctas ? cap_ctas : want));
     const unsigned long long timeout_ns = (unsigned long long)(pg->timeout_ms > 0 ? pg->timeout_ms : 20000) * 1000000ull;
-    const unsigned arrivals = push_ctas(total);
-#define PX_LAUNCH(T) peer_finish_kernel<T><<<grid, PX_THREADS, 0, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, arrivals, timeout_ns)
+#define PX_LAUNCH(T) peer_finish_kernel<T><<<grid, PX_THREADS, 0, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, timeout_ns)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
     else if (dtype == SPX_F32) PX_LAUNCH(float);
@@ -228,7 +244,7 @@ using namespace spx;
 
 extern "C" size_t spx_peer_buffer_bytes(size_t capacity_bytes, int world) {
     if (world < 1 || world > SPX_MAX_PEERS) return 0;
-    return PEER_DATA + 2 * (size_t)world * align_up(capacity_bytes, 16);
+    return PEER_DATA + 2 * align_up(capacity_bytes, 16);
 }
 
 extern "C" int spx_peer_buffer_create(size_t capacity_bytes, int world, void **buffer, unsigned char handle[64]) {

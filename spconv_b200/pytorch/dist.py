@@ -107,7 +107,7 @@ class PeerGroup:
         ...
         loss.backward()                           # no all-reduce call, no gradient bucket
 
-    Every rank allocates one buffer (``2 x world x capacity`` bytes), exports a CUDA IPC handle, and maps
+    Every rank allocates one buffer (``2 x capacity`` bytes: two epochs of its own fp32 slices), exports a CUDA IPC handle, and maps
     the others' (NVLink peer access).  ``capacity_bytes`` bounds the largest weight tensor, counted as
     fp32 (default 8 MB = 27 x 256 x 256 and some).  ``scale`` multiplies the sum (``1 / world`` = mean, the
     DDP convention).  Raises if peer mapping is not possible -- callers that can live without the fused
