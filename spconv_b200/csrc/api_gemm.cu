@@ -133,7 +133,10 @@ static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void 
         SPX_CHECK_CUDA(cudaMemsetAsync(dfilters, 0, (size_t)dw_count * dtype_bytes(d->dtype), (cudaStream_t)stream));
         if (pg) {
             if (int rc = peer_push(nullptr, 0, 0, dfilters, dw_count, d->dtype, pg, (cudaStream_t)stream)) return rc;
-            if (finish) return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+            if (finish) {
+                if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
+                return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+            }
         }
         return 0;
     }
@@ -153,14 +156,20 @@ static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void 
                     "implicit_gemm_wgrad: workspace too small (%zu < %zu)", workspace_bytes, tc_wgrad_workspace_size(w));
         set_family(2);
         if (int rc = tc_wgrad(w, (cudaStream_t)stream)) return rc;     // with peers: partial sums pushed, dW not written yet
-        if (pg && finish) return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+        if (pg && finish) {
+            if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
+            return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+        }
         return 0;
     }
     set_family(1);
     if (int rc = simt_wgrad(w, (cudaStream_t)stream)) return rc;
     if (pg) {
         if (int rc = peer_push(nullptr, 0, 0, dfilters, dw_count, d->dtype, pg, (cudaStream_t)stream)) return rc;
-        if (finish) return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+        if (finish) {
+            if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
+            return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
+        }
     }
     return 0;
 }

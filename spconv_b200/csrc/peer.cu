@@ -78,7 +78,7 @@ constexpr int PX_THREADS = 256, PX_WARPS = PX_THREADS / 32;
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
 peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, const T *__restrict__ src, int64_t total,
-                 PeerPtrs peers, int world, int rank, int64_t capacity) {
+                 PeerPtrs peers, int world, int rank, int64_t capacity, int defer_signal) {
     __shared__ float4 acc_s[PX_WARPS][32];
     __shared__ unsigned s_epoch;
     PeerState *st = reinterpret_cast<PeerState *>(peers.buf[rank]);
@@ -117,6 +117,7 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     }
     if (i < total)                                         // the padded tail of the last float4 carries zeros
         *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.buf[rank] + PEER_DATA) + (int64_t)(epoch & 1u) * capacity + i) = t;
+    if (defer_signal) return;                              // peer_signal_kernel publishes (A/B: debug bit 8192)
     __threadfence();
     __syncwarp();
     unsigned last = 0;
@@ -127,6 +128,15 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     __threadfence_system();
     if (lane == 0) st->done = 0;
     if (lane < world) st_release_sys(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_FLAGS) + rank, epoch + 1u);
+}
+
+// the publish step on its own (one warp): everything earlier in the stream is complete, make it visible
+// system-wide and store the epoch into every rank's flag word
+__global__ void peer_signal_kernel(PeerPtrs peers, int world, int rank) {
+    const unsigned epoch = reinterpret_cast<const PeerState *>(peers.buf[rank])->epoch;
+    __threadfence_system();
+    if ((int)threadIdx.x < world)
+        st_release_sys(reinterpret_cast<unsigned *>(peers.buf[threadIdx.x] + PEER_FLAGS) + rank, epoch + 1u);
 }
 
 template <typename T>
@@ -207,13 +217,21 @@ int peer_push(const float *partial, int64_t stride, int chunks, const void *src,
     const PeerPtrs pp = peer_ptrs(pg);
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
     const unsigned grid = push_ctas(total);
-#define PX_LAUNCH(T) peer_push_kernel<T><<<grid, PX_THREADS, 0, stream>>>(partial, stride, chunks, (const T *)src, total, pp, pg->world, pg->rank, cap)
+    const int defer = (runtime_cfg().debug & 8192) ? 1 : 0;
+#define PX_LAUNCH(T) peer_push_kernel<T><<<grid, PX_THREADS, 0, stream>>>(partial, stride, chunks, (const T *)src, total, pp, pg->world, pg->rank, cap, defer)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
     else if (dtype == SPX_F32) PX_LAUNCH(float);
     else { set_error("peer push: dtype %d not supported", dtype); return 2; }
 #undef PX_LAUNCH
     SPX_CHECK_LAUNCH("peer_push_kernel");
+    return 0;
+}
+
+int peer_signal(const spx_peer_group *pg, cudaStream_t stream) {
+    if (int rc = check_group(pg, 0, "peer signal")) return rc;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer_ptrs(pg), pg->world, pg->rank);
+    SPX_CHECK_LAUNCH("peer_signal_kernel");
     return 0;
 }
 
@@ -300,6 +318,12 @@ extern "C" int spx_peer_push(const spx_peer_group *pg, const void *data, int64_t
     return peer_push(nullptr, 0, 0, data, count, dtype, pg, (cudaStream_t)stream);
 }
 
+/* only with spx_debug_configure bit 8192 (the reduction kernel does not publish): publish what has been
+ * pushed on this stream so far */
+extern "C" int spx_peer_signal(const spx_peer_group *pg, spx_stream_t stream) {
+    return peer_signal(pg, (cudaStream_t)stream);
+}
+
 extern "C" int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t count, int dtype, float scale,
                                spx_stream_t stream) {
     SPX_REQUIRE(out != nullptr || count == 0, "peer_finish: out is NULL");
@@ -309,5 +333,6 @@ extern "C" int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t coun
 extern "C" int spx_peer_allreduce(const spx_peer_group *pg, void *data, int64_t count, int dtype, float scale,
                                   spx_stream_t stream) {
     if (int rc = spx_peer_push(pg, data, count, dtype, stream)) return rc;
+    if (runtime_cfg().debug & 8192) if (int rc = spx_peer_signal(pg, stream)) return rc;
     return spx_peer_finish(pg, data, count, dtype, scale, stream);
 }

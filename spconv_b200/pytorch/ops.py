@@ -652,24 +652,29 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
 
     def finish_exchange():
         with timer.record("implicit_gemm_wgrad_exchange", _stream()):
+            if _PEERS.defer_signal:
+                _cabi.check(lib.spx_peer_signal(ctypes.byref(_PEERS.group), _stream()), "peer_signal")
             _cabi.check(lib.spx_peer_finish(ctypes.byref(_PEERS.group), _ptr(dfilters), dfilters.numel(),
                                             _DTYPE_CODE[dfilters.dtype], _PEERS.scale, _stream()), "peer_finish")
 
     if _PEERS is not None:
-        # push first, the input gradient hides the NVLink latency, then the local rank-order sum
         if timer.enable or not (n_in and n_out) or not torch._C._cuda_isCurrentStreamCapturing():
+            # eager: one stream (a fork / join per layer costs more host time than it hides); the input gradient
+            # between publish and finish hides the NVLink latency
             run_wgrad()
             run_dgrad()
             finish_exchange()
             return din, dfilters
+        # captured: weight gradient + publish, then the receive side (wait, pull, rank-order sum) on a forked stream
+        # BESIDE the input gradient -- the exchange is off the critical path like a DDP hook's all-reduce
         main = torch.cuda.current_stream()
         side = _side_stream(features.device)
-        side.wait_stream(main)
         run_wgrad()
+        side.wait_stream(main)
         with torch.cuda.stream(side):
-            run_dgrad()
+            finish_exchange()
+        run_dgrad()
         main.wait_stream(side)
-        finish_exchange()
         return din, dfilters
     if _WGRAD_HOOK is not None and n_in and n_out:
         # Data-parallel overlap: weight gradient FIRST, then the hook (typically the all-reduce of dW) on

@@ -71,12 +71,17 @@ def test_world_of_one_equals_the_plain_weight_gradient(cuda_dev, no_peers):
     pg.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_ranks_on_one_gpu_exchange_through_the_fused_kernel(world, cuda_dev, no_peers):
-    """world ranks = world streams; every rank's kernel pushes into all buffers and waits for the others"""
+@pytest.mark.parametrize("world,defer", [(2, False), (3, False), (2, True)], ids=["2", "3", "2-separate-publish"])
+def test_ranks_on_one_gpu_exchange_through_the_fused_kernel(world, defer, cuda_dev, no_peers):
+    """world ranks = world streams: every rank's reduction kernel publishes its slices, every finish pulls them all.
+    defer: the A/B variant where a one-warp kernel publishes (spx_debug_configure bit 8192)."""
+    from spconv_b200 import _cabi
     from spconv_b200.pytorch import ops
     from spconv_b200.pytorch.dist import PeerGroup
     ring = PeerGroup.local_ring(world, capacity_bytes=1 << 20, average=True)
+    _cabi.check(_cabi.load().spx_debug_configure(-1, 0, 8192 if defer else 0, None, 0), "debug_configure")
+    for pg in ring:
+        pg.defer_signal = defer
     streams = [torch.cuda.Stream() for _ in range(world)]
     cases = [(64, 64, True, torch.float16), (64, 128, False, torch.bfloat16), (32, 32, True, torch.float16),
              (48, 24, True, torch.float16), (64, 64, True, torch.float16)]       # K=24: FMA kernel + standalone exchange
@@ -100,6 +105,7 @@ def test_ranks_on_one_gpu_exchange_through_the_fused_kernel(world, cuda_dev, no_
         # one rounding of the fp32 sum vs the mean of `world` separately rounded gradients
         tol = ulp * (sum(d.float().abs() for d in local) / world + want.abs()) + 1e-6
         assert (got - want).abs().le(tol).all(), (it, float((got - want).abs().max()))
+    _cabi.check(_cabi.load().spx_debug_configure(-1, 0, 0, None, 0), "debug_configure")
     assert all(pg.error() == 0 for pg in ring)
     for pg in ring:
         pg.close()
