@@ -51,6 +51,8 @@ def no_peers():
     from spconv_b200.pytorch import ops
     yield
     ops.set_peer_group(None)
+    from spconv_b200 import _cabi
+    _cabi.check(_cabi.load().spx_debug_configure(-1, 0, 0, None, 0), "debug_configure")
 
 
 def test_world_of_one_equals_the_plain_weight_gradient(cuda_dev, no_peers):
