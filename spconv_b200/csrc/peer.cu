@@ -166,12 +166,16 @@ peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world
     const float nan = __int_as_float(0x7fc00000);
     for (int64_t g = (int64_t)blockIdx.x * PX_THREADS + threadIdx.x; g < n4; g += (int64_t)gridDim.x * PX_THREADS) {
         const int64_t i = g * 4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {                  // rank order: identical bits on every rank
-            const float4 v = ld_relaxed_sys_f4(reinterpret_cast<const float *>(peers.buf[r] + PEER_DATA) + slot_off + i);
-            if (r == 0) t = v;
-            else { t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
-        }
+        // all loads first (one NVLink round trip for the whole world, not one per rank: a warp issues in order and
+        // would stall on the first add), then the sum in rank order: identical bits on every rank
+        float4 v[SPX_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < SPX_MAX_PEERS; ++r)
+            if (r < world) v[r] = ld_relaxed_sys_f4(reinterpret_cast<const float *>(peers.buf[r] + PEER_DATA) + slot_off + i);
+        float4 t = v[0];
+#pragma unroll
+        for (int r = 1; r < SPX_MAX_PEERS; ++r)
+            if (r < world) { t.x += v[r].x; t.y += v[r].y; t.z += v[r].z; t.w += v[r].w; }
         if (bad) t = make_float4(nan, nan, nan, nan);
         dst[i] = from_float<T>(t.x * scale);
         if (i + 1 < total) dst[i + 1] = from_float<T>(t.y * scale);
@@ -242,7 +246,7 @@ int peer_finish(void *dst, int64_t total, int dtype, const spx_peer_group *pg, f
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
     // a few co-resident CTAs: the wait is normally over before they start.  Ranks that share one device
     // (single-GPU protocol tests) must leave the SMs to each other's weight-gradient CTAs.
-    int64_t want = div_up64(div_up64(total, 4), PX_THREADS * 2);
+    int64_t want = div_up64(div_up64(total, 4), PX_THREADS);
     const int64_t cap_ctas = pg->colocated > 1 ? (sm_count() / (4 * pg->colocated) > 0 ? sm_count() / (4 * pg->colocated) : 1) : sm_count();
     const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap_ctas ? cap_ctas : want));
     const unsigned long long timeout_ns = (unsigned long long)(pg->timeout_ms > 0 ? pg->timeout_ms : 20000) * 1000000ull;
