@@ -139,15 +139,26 @@ __global__ void peer_signal_kernel(PeerPtrs peers, int world, int rank) {
         st_release_sys(reinterpret_cast<unsigned *>(peers.buf[threadIdx.x] + PEER_FLAGS) + rank, epoch + 1u);
 }
 
+// Receive side.  It runs BESIDE the persistent input-gradient kernel (whose CTAs own most of every SM's register
+// file) and may have to wait for a slower rank, so its footprint must be tiny: a handful of CTAs, and the pulls are
+// TMA bulk copies (cp.async.bulk global -> shared over the peer mapping, mbarrier completion) issued by one thread --
+// bytes in flight without registers.  A first version (one thread per float4, ~100 CTAs x 26 k registers, spinning
+// on the flags) kept the input-gradient CTAs off its SMs for as long as the slowest rank was late: +22 us per
+// pipelined config-2 step at N = 2 (profiles/README.md, session n2e).
+constexpr int FIN_CHUNK_BYTES = 8192;              // per source rank per step: world x 8 KB in flight per CTA
+constexpr int FIN_MAX_CTAS = 16;
+
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
 peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world, int rank, int64_t capacity, float scale,
                    unsigned long long timeout_ns) {
+    extern __shared__ __align__(128) uint8_t fin_smem[];      // [world][FIN_CHUNK_BYTES] + mbarrier
+    __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned s_epoch;
     __shared__ int s_bad;
     char *mine = peers.buf[rank];
     PeerState *st = reinterpret_cast<PeerState *>(mine);
-    if (threadIdx.x == 0) { s_epoch = st->epoch; s_bad = 0; }
+    if (threadIdx.x == 0) { s_epoch = st->epoch; s_bad = 0; mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     const unsigned epoch = s_epoch, target = epoch + 1u;
     if (threadIdx.x < world) {
@@ -155,35 +166,47 @@ peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
         while ((int)(ld_acquire_sys(flag) - target) < 0) {
-            if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) { s_bad = 1; break; }
+            __nanosleep(200);
+            if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > timeout_ns) { s_bad = 1; break; }
         }
     }
     __syncthreads();
     const bool bad = s_bad != 0;
     if (bad && threadIdx.x == 0) st->error = 1u;
     const int64_t slot_off = (int64_t)(epoch & 1u) * capacity;
-    const int64_t n4 = (total + 3) / 4;
+    const int64_t padded = (total + 3) / 4 * 4;                       // floats every publisher wrote
+    const int64_t chunk_floats = FIN_CHUNK_BYTES / 4;
+    const int64_t nchunks = (padded + chunk_floats - 1) / chunk_floats;
     const float nan = __int_as_float(0x7fc00000);
-    for (int64_t g = (int64_t)blockIdx.x * PX_THREADS + threadIdx.x; g < n4; g += (int64_t)gridDim.x * PX_THREADS) {
-        const int64_t i = g * 4;
-        // all loads first (one NVLink round trip for the whole world, not one per rank: a warp issues in order and
-        // would stall on the first add), then the sum in rank order: identical bits on every rank
-        float4 v[SPX_MAX_PEERS];
-#pragma unroll
-        for (int r = 0; r < SPX_MAX_PEERS; ++r)
-            if (r < world) v[r] = ld_relaxed_sys_f4(reinterpret_cast<const float *>(peers.buf[r] + PEER_DATA) + slot_off + i);
-        float4 t = v[0];
-#pragma unroll
-        for (int r = 1; r < SPX_MAX_PEERS; ++r)
-            if (r < world) { t.x += v[r].x; t.y += v[r].y; t.z += v[r].z; t.w += v[r].w; }
-        if (bad) t = make_float4(nan, nan, nan, nan);
-        dst[i] = from_float<T>(t.x * scale);
-        if (i + 1 < total) dst[i + 1] = from_float<T>(t.y * scale);
-        if (i + 2 < total) dst[i + 2] = from_float<T>(t.z * scale);
-        if (i + 3 < total) dst[i + 3] = from_float<T>(t.w * scale);
+    uint32_t phase = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t f0 = c * chunk_floats;
+        const int nfl = (int)((padded - f0) < chunk_floats ? (padded - f0) : chunk_floats);
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");          // flags acquired / smem consumed in the generic proxy
+            mbar_arrive_expect_tx(&bar, (uint32_t)(world * nfl * 4));
+            for (int r = 0; r < world; ++r)
+                bulk_copy_g2s(smem_u32(fin_smem + (size_t)r * FIN_CHUNK_BYTES),
+                              reinterpret_cast<const float *>(peers.buf[r] + PEER_DATA) + slot_off + f0, (uint32_t)(nfl * 4), &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        for (int j = threadIdx.x * 4; j < nfl; j += PX_THREADS * 4) {
+            float4 t = *reinterpret_cast<const float4 *>(fin_smem + (size_t)j * 4);
+            for (int r = 1; r < world; ++r) {                          // rank order: identical bits on every rank
+                const float4 v = *reinterpret_cast<const float4 *>(fin_smem + (size_t)r * FIN_CHUNK_BYTES + (size_t)j * 4);
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+            }
+            if (bad) t = make_float4(nan, nan, nan, nan);
+            const int64_t i = f0 + j;
+            dst[i] = from_float<T>(t.x * scale);
+            if (i + 1 < total) dst[i + 1] = from_float<T>(t.y * scale);
+            if (i + 2 < total) dst[i + 2] = from_float<T>(t.z * scale);
+            if (i + 3 < total) dst[i + 3] = from_float<T>(t.w * scale);
+        }
+        __syncthreads();                                               // the chunk is consumed before it is overwritten
     }
     // ---- the last CTA out advances the epoch (publish / finish of one group alternate in stream order)
-    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {
@@ -244,13 +267,20 @@ int peer_finish(void *dst, int64_t total, int dtype, const spx_peer_group *pg, f
     if (total == 0) return 0;
     const PeerPtrs pp = peer_ptrs(pg);
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
-    // a few co-resident CTAs: the wait is normally over before they start.  Ranks that share one device
-    // (single-GPU protocol tests) must leave the SMs to each other's weight-gradient CTAs.
-    int64_t want = div_up64(div_up64(total, 4), PX_THREADS);
-    const int64_t cap_ctas = pg->colocated > 1 ? (sm_count() / (4 * pg->colocated) > 0 ? sm_count() / (4 * pg->colocated) : 1) : sm_count();
-    const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap_ctas ? cap_ctas : want));
+    const int64_t nchunks = div_up64((total + 3) / 4 * 16, FIN_CHUNK_BYTES);
+    int64_t max_ctas = FIN_MAX_CTAS;
+    if (pg->colocated > 1 && max_ctas > FIN_MAX_CTAS / pg->colocated) max_ctas = FIN_MAX_CTAS / pg->colocated > 0 ? FIN_MAX_CTAS / pg->colocated : 1;
+    const unsigned grid = (unsigned)(nchunks < max_ctas ? nchunks : max_ctas);
+    const size_t smem = (size_t)pg->world * FIN_CHUNK_BYTES;
     const unsigned long long timeout_ns = (unsigned long long)(pg->timeout_ms > 0 ? pg->timeout_ms : 20000) * 1000000ull;
-#define PX_LAUNCH(T) peer_finish_kernel<T><<<grid, PX_THREADS, 0, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, timeout_ns)
+#define PX_LAUNCH(T)                                                                                                  \
+    do {                                                                                                              \
+        auto fn = peer_finish_kernel<T>;                                                                              \
+        if (smem > 48 * 1024 && !func_configured((const void *)fn, current_device()))                                 \
+            SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                                SPX_MAX_PEERS * FIN_CHUNK_BYTES));                                    \
+        fn<<<grid, PX_THREADS, smem, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, timeout_ns);     \
+    } while (0)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
     else if (dtype == SPX_F32) PX_LAUNCH(float);
