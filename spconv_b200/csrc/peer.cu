@@ -117,14 +117,21 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     }
     if (i < total)                                         // the padded tail of the last float4 carries zeros
         *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.buf[rank] + PEER_DATA) + (int64_t)(epoch & 1u) * capacity + i) = t;
-    if (defer_signal) return;                              // peer_signal_kernel publishes (A/B: debug bit 8192)
+    if (defer_signal & 1) return;                          // peer_signal_kernel publishes (A/B: debug bit 8192)
     __threadfence();
     __syncwarp();
     unsigned last = 0;
     if (lane == 0) last = atomicAdd(&st->done, 1u) == gridDim.x - 1 ? 1u : 0u;
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    // every slice of this rank is in its buffer: one system-scope fence, then tell everybody
+    // every slice of this rank is in its buffer (= visible in this GPU's L2, where the peers' reads arrive): tell everybody
+    if (defer_signal & 2) {                                // A/B (debug bit 16384): gpu-scope fence + plain system-scope flag store
+        __threadfence();
+        if (lane == 0) st->done = 0;
+        if (lane < world)
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_FLAGS) + rank), "r"(epoch + 1u) : "memory");
+        return;
+    }
     __threadfence_system();
     if (lane == 0) st->done = 0;
     if (lane < world) st_release_sys(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_FLAGS) + rank, epoch + 1u);
@@ -244,7 +251,7 @@ int peer_push(const float *partial, int64_t stride, int chunks, const void *src,
     const PeerPtrs pp = peer_ptrs(pg);
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
     const unsigned grid = push_ctas(total);
-    const int defer = (runtime_cfg().debug & 8192) ? 1 : 0;
+    const int defer = ((runtime_cfg().debug & 8192) ? 1 : 0) | ((runtime_cfg().debug & 16384) ? 2 : 0);
 #define PX_LAUNCH(T) peer_push_kernel<T><<<grid, PX_THREADS, 0, stream>>>(partial, stride, chunks, (const T *)src, total, pp, pg->world, pg->rank, cap, defer)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
