@@ -153,7 +153,7 @@ __global__ void peer_signal_kernel(PeerPtrs peers, int world, int rank) {
 // on the flags) kept the input-gradient CTAs off its SMs for as long as the slowest rank was late: +22 us per
 // pipelined config-2 step at N = 2 (profiles/README.md, session n2e).
 constexpr int FIN_CHUNK_BYTES = 8192;              // per source rank per step: world x 8 KB in flight per CTA
-constexpr int FIN_MAX_CTAS = 16;
+constexpr int FIN_MAX_CTAS = 64;               // 0.44 MB per peer = 54 chunks: one round trip for the whole tensor
 
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
