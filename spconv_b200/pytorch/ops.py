@@ -72,6 +72,20 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     return st
 
 
+_EXCHANGE_STREAMS: dict = {}
+
+
+def _exchange_stream(device: torch.device) -> "torch.cuda.Stream":
+    """High-priority auxiliary stream for the receive side of the weight-gradient exchange: its few small CTAs
+    must not queue behind the rulebook kernels of the next cloud or the persistent input-gradient CTAs (NCCL runs
+    its collectives on high-priority streams for the same reason)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _EXCHANGE_STREAMS.get(key)
+    if st is None:
+        st = _EXCHANGE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
+    return st
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None or t.numel() == 0:
         return None
@@ -668,7 +682,7 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         # captured: weight gradient + publish, then the receive side (wait, pull, rank-order sum) on a forked stream
         # BESIDE the input gradient -- the exchange is off the critical path like a DDP hook's all-reduce
         main = torch.cuda.current_stream()
-        side = _side_stream(features.device)
+        side = _exchange_stream(features.device)
         run_wgrad()
         side.wait_stream(main)
         with torch.cuda.stream(side):
