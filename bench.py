@@ -86,7 +86,7 @@ def parse_args():
                          "3 = 2 + the eager encoder prefetches its whole rulebook chain from a worker thread")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
-    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl", "fused-local"],
                     help="N > 1: dW all-reduce fused into the weight-gradient kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
     ap.add_argument("--debug-bits", type=int, default=0,
@@ -247,6 +247,11 @@ class Ctx:
         # N > 1: the all-reduce of dW is the tail of the weight-gradient kernel (NVLink peer stores, csrc/peer.cu);
         # --allreduce nccl keeps the library collective for A/B.  All ranks agree on which one runs.
         self.peers = None
+        if self.world > 1 and args.allreduce == "fused-local":
+            # triage only: every rank exchanges with itself (world-of-one group) -- the kernels of the fused path
+            # without the cross-rank dependency
+            from spconv_b200.pytorch.dist import PeerGroup
+            self.peers = PeerGroup.local_ring(1, capacity_bytes=8 << 20, average=False)[0]
         if self.world > 1 and args.allreduce == "fused":
             from spconv_b200.pytorch.dist import PeerGroup
             ok = torch.ones(1, device=self.dev, dtype=torch.int32)

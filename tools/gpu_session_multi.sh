@@ -18,9 +18,9 @@ except Exception as e:
     print("$1 FAILED", e)
 PY
 }
-(timeout 300 python -m pytest tests/test_peer_gpu.py -m gpu -q 2>&1 | tail -15) > $O/${TAG}_tests.log; tail -3 $O/${TAG}_tests.log | cut -c1-300
 (timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/peer_check.py > $O/${TAG}_peer_check.log 2>&1); grep -v Warning $O/${TAG}_peer_check.log | tail -4 | cut -c1-400
 run bench "--extras 0"
+run bench_local "--allreduce fused-local --extras 0"
 run bench_nccl "--allreduce nccl --extras 0"
 (timeout 200 python bench.py --gpus 1 --extras 0 > $O/${TAG}_bench_n1.json 2>> $O/${TAG}_bench.err); python -c "import json; d=json.loads(open('$O/${TAG}_bench_n1.json').read().strip().splitlines()[-1]); print('N=1 same box', d['value']/1e6, d['ms_per_step'])"
 echo "== done $(date -u +%H:%M:%S)"
