@@ -88,6 +88,8 @@ def parse_args():
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl", "fused-local"],
                     help="N > 1: dW all-reduce fused into the weight-gradient kernel over NVLink peer memory, or NCCL")
+    ap.add_argument("--peer-triage", type=int, default=0, help="triage of the fused exchange: 1 skip finish, 2 plain "
+                    "weight gradient + finish only, 4 finish on the launching stream")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
     ap.add_argument("--debug-bits", type=int, default=0,
                     help="spx_debug_configure bits for A/B runs (64 onesweep sort, 128 round-1 conv rulebook, "
@@ -241,13 +243,14 @@ class Ctx:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+        ops._PEER_TRIAGE = int(args.peer_triage)
         if args.debug_bits:
             from spconv_b200 import _cabi
             _cabi.check(_cabi.load().spx_debug_configure(-1, 0, int(args.debug_bits), None, 0), "debug_configure")
         # N > 1: the all-reduce of dW is the tail of the weight-gradient kernel (NVLink peer stores, csrc/peer.cu);
         # --allreduce nccl keeps the library collective for A/B.  All ranks agree on which one runs.
         self.peers = None
-        if self.world > 1 and args.allreduce == "fused-local":
+        if args.allreduce == "fused-local":
             # triage only: every rank exchanges with itself (world-of-one group) -- the kernels of the fused path
             # without the cross-rank dependency
             from spconv_b200.pytorch.dist import PeerGroup
@@ -613,7 +616,7 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     world = ctx.world
     clouds = w.clouds
     train = not w.inference
-    fused_ar = world > 1 and train and ctx.peers is not None
+    fused_ar = train and ctx.peers is not None
     if fused_ar:
         ops.set_peer_group(ctx.peers)            # every dW leaves its kernel already summed over the ranks
     elif world > 1 and train and hasattr(w, "install_allreduce_hook"):

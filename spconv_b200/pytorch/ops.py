@@ -653,7 +653,7 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
 
     def run_wgrad():
         with timer.record("implicit_gemm_wgrad", _stream()):
-            if _PEERS is not None:
+            if _PEERS is not None and not (_PEER_TRIAGE & 2):
                 # data-parallel: the kernel that reduces the split-K partials pushes this rank's fp32 dW into every
                 # rank's exchange buffer (csrc/peer.cu); finish_exchange() below writes dfilters
                 _cabi.check(lib.spx_implicit_gemm_wgrad_push(
@@ -665,6 +665,8 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
                                                         _stream()), "implicit_gemm_wgrad")
 
     def finish_exchange():
+        if _PEER_TRIAGE & 1:
+            return
         with timer.record("implicit_gemm_wgrad_exchange", _stream()):
             if _PEERS.defer_signal:
                 _cabi.check(lib.spx_peer_signal(ctypes.byref(_PEERS.group), _stream()), "peer_signal")
@@ -684,6 +686,10 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         main = torch.cuda.current_stream()
         side = _exchange_stream(features.device)
         run_wgrad()
+        if _PEER_TRIAGE & 4:
+            run_dgrad()
+            finish_exchange()
+            return din, dfilters
         side.wait_stream(main)
         with torch.cuda.stream(side):
             finish_exchange()
@@ -736,6 +742,7 @@ def set_wgrad_hook(fn) -> None:
 
 
 _PEERS = None
+_PEER_TRIAGE = 0          # bench.py --peer-triage (timing experiments only; results are wrong when set)
 
 
 def set_peer_group(peers) -> None:
