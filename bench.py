@@ -369,6 +369,8 @@ class LayerWorkload(Workload):
         self.weight2 = (self.weight * 0.5).contiguous()      # second layer of the indice_key-reuse leg
         self.grad_buf = torch.zeros_like(self.weight)         # what the all-reduce / D2H read
         self.hooked = False
+        self.direct = False                                   # fused exchange: dW leaves backward final, no copy into grad_buf
+        self.last_dw = None
         for c in self.clouds:
             res = self.rulebook(c)
             c["m"] = res[0].shape[0]
@@ -398,14 +400,19 @@ class LayerWorkload(Workload):
         dw = None
         for j in range(calls):
             _, _, dw = self.conv_fwd_bwd(c, res, self.weight if j == 0 else self.weight2, kw)
-        if not self.hooked:
-            self.grad_buf.copy_(dw)
+        self.keep(dw)
         return dw
 
     def compute(self, c, res):
         """forward + backward on an already built rulebook (the second stage of the pipelined replay)"""
         _, _, dw = self.conv_fwd_bwd(c, res, self.weight, {})
-        if not self.hooked:
+        self.keep(dw)
+
+    def keep(self, dw):
+        """what the step's all-reduce / D2H read: the gradient buffer, or (fused exchange) the reduced dW itself"""
+        if self.direct:
+            self.last_dw = dw
+        elif not self.hooked:
             self.grad_buf.copy_(dw)
 
     def install_allreduce_hook(self):
@@ -420,7 +427,7 @@ class LayerWorkload(Workload):
         self.hooked = True
 
     def grads(self):
-        return self.grad_buf
+        return self.last_dw if self.direct and self.last_dw is not None else self.grad_buf
 
     def make_input(self, d_inds, d_feats):
         return self.ctx.spconv.SparseConvTensor(d_feats.detach().requires_grad_(True), d_inds, self.wl["shape"],
@@ -431,8 +438,7 @@ class LayerWorkload(Workload):
         y = self.layer(x)
         loss = y.features.square().mean(dtype=self.ctx.torch.float32)
         loss.backward()
-        if not self.hooked:
-            self.grad_buf.copy_(self.layer.weight.grad)
+        self.keep(self.layer.weight.grad)
         return loss
 
     def config(self):
@@ -619,9 +625,14 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     fused_ar = train and ctx.peers is not None
     if fused_ar:
         ops.set_peer_group(ctx.peers)            # every dW leaves its kernel already summed over the ranks
+
     elif world > 1 and train and hasattr(w, "install_allreduce_hook"):
         w.install_allreduce_hook()               # all-reduce(dW) beside the input gradient of the same step
     explicit_ar = world > 1 and train and not fused_ar and not getattr(w, "hooked", False)
+    if hasattr(w, "direct"):
+        # nothing reads a separate gradient buffer unless NCCL reduces it: the step's dW itself is what the D2H of the
+        # e2e legs reads (autograd does the same: the first accumulation takes the tensor, it does not copy it)
+        w.direct = train and not explicit_ar and not getattr(w, "hooked", False)
 
     # ---------------- warm-up (also configures kernels / NCCL before any graph capture)
     for i in range(max(warmup, 3)):

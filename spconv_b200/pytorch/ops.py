@@ -669,15 +669,17 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
             return din, dfilters
         # captured: the two gradients stay parallel branches as in the single-GPU graph (measured: running them one
         # after the other costs 17 us per config-2 step, more than the whole exchange).  Weight gradient + publish
-        # on the caller's stream, input gradient on the forked one; the receive side (wait, TMA pull, rank-order
-        # sum: a few small CTAs) follows the publish and overlaps the tail of the input gradient.
+        # on the caller's stream, input gradient on the forked one, the receive side (wait, TMA pull, rank-order
+        # sum: a few small CTAs) behind it: every dependent kernel on the caller's stream costs ~8 us of launch and
+        # queueing when the next cloud's rulebook kernels share the GPU.
         main = torch.cuda.current_stream()
         side = _side_stream(features.device)
         side.wait_stream(main)
         run_wgrad()
         with torch.cuda.stream(side):
             run_dgrad()
-        finish_exchange()
+            side.wait_stream(main)          # the publish
+            finish_exchange()
         main.wait_stream(side)
         return din, dfilters
     if _WGRAD_HOOK is not None and n_in and n_out:
@@ -685,15 +687,6 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         # a forked stream while the input gradient -- which the hook does not need -- runs on this one.
         main = torch.cuda.current_stream()
         side = _side_stream(features.device)
-        if torch._C._cuda_isCurrentStreamCapturing() and not timer.enable:
-            # captured: both gradients as parallel branches (see above), the hook right behind the weight gradient
-            side.wait_stream(main)
-            run_wgrad()
-            with torch.cuda.stream(side):
-                run_dgrad()
-            _WGRAD_HOOK(dfilters)
-            main.wait_stream(side)
-            return din, dfilters
         run_wgrad()
         side.wait_stream(main)
         with torch.cuda.stream(side):
