@@ -267,8 +267,6 @@ class Ctx:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 self.peers = None
-            elif int(args.debug_bits) & 8192:            # A/B: publish from a separate one-warp kernel
-                self.peers.defer_signal = True
         self.flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=self.dev)
         self.side = torch.cuda.Stream()
         self.side2 = torch.cuda.Stream()

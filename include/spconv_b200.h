@@ -299,9 +299,6 @@ int spx_implicit_gemm_wgrad_allreduce(const spx_gemm_desc *d, const void *featur
 /* the same exchange for an existing small tensor (bias gradients ...): push sends `data` (dtype SPX_F32 /
  * SPX_F16 / SPX_BF16), finish writes out = scale * sum over ranks (out may be data); allreduce = both */
 int spx_peer_push(const spx_peer_group *pg, const void *data, int64_t count, int dtype, spx_stream_t stream);
-/* A/B variant (spx_debug_configure bit 8192): the reduction kernel only writes the slices, this one-warp
- * kernel publishes them */
-int spx_peer_signal(const spx_peer_group *pg, spx_stream_t stream);
 int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t count, int dtype, float scale, spx_stream_t stream);
 int spx_peer_allreduce(const spx_peer_group *pg, void *data, int64_t count, int dtype, float scale,
                        spx_stream_t stream);

@@ -104,7 +104,6 @@ SIGNATURES = {
     "spx_implicit_gemm_wgrad_push": (c_int, [POINTER(GemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                              POINTER(PeerGroup), c_void_p]),
     "spx_peer_push": (c_int, [POINTER(PeerGroup), c_void_p, c_int64, c_int, c_void_p]),
-    "spx_peer_signal": (c_int, [POINTER(PeerGroup), c_void_p]),
     "spx_peer_finish": (c_int, [POINTER(PeerGroup), c_void_p, c_int64, c_int, c_float, c_void_p]),
     "spx_peer_allreduce": (c_int, [POINTER(PeerGroup), c_void_p, c_int64, c_int, c_float, c_void_p]),
     "spx_bias_act_inplace": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float,

@@ -134,7 +134,6 @@ static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void 
         if (pg) {
             if (int rc = peer_push(nullptr, 0, 0, dfilters, dw_count, d->dtype, pg, (cudaStream_t)stream)) return rc;
             if (finish) {
-                if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
                 return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
             }
         }
@@ -157,7 +156,6 @@ static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void 
         set_family(2);
         if (int rc = tc_wgrad(w, (cudaStream_t)stream)) return rc;     // with peers: partial sums pushed, dW not written yet
         if (pg && finish) {
-            if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
             return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
         }
         return 0;
@@ -167,7 +165,6 @@ static int wgrad_entry(const spx_gemm_desc *d, const void *features, const void 
     if (pg) {
         if (int rc = peer_push(nullptr, 0, 0, dfilters, dw_count, d->dtype, pg, (cudaStream_t)stream)) return rc;
         if (finish) {
-            if (runtime_cfg().debug & 8192) if (int rc = peer_signal(pg, (cudaStream_t)stream)) return rc;
             return peer_finish(dfilters, dw_count, d->dtype, pg, scale, (cudaStream_t)stream);
         }
     }

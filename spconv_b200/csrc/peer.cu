@@ -2,37 +2,43 @@
 //
 // The only tensor that crosses GPUs on this path is dW (the reference itself has no
 // distributed code).  dW is small (27*C*K values: 0.4 MB fp32 at C = K = 64), so the exchange is
-// latency-bound and a library all-reduce costs more in launches and protocol than in bytes.  Here the
-// send side is the tail of the weight-gradient reduction itself and the receive side is one small kernel:
+// latency-bound and a library all-reduce costs more in launches and protocol than in bytes.  Two kernels:
 //
-//   publish (peer_push_kernel = the kernel that reduces the split-K partials of tc_wgrad_kernel, or reads
-//           an existing gradient): every CTA sums its 128-value slice in fp32 and writes it to this rank's
-//           OWN exchange buffer [slot][element] -- local stores, gpu-scope fence, one local counter.  The
-//           LAST CTA out makes the slices visible system-wide (one fence.sys per kernel) and stores the
-//           epoch into every rank's flag word for this source (world tiny release stores over NVLink).
-//           Never waits.
-//   finish  (peer_finish_kernel): waits until every source's flag shows this epoch (acquire loads on its
-//           OWN flags), reads the world's slices -- its own locally, the others through the peer mapping
-//           -- and sums them in rank order: the same order on every rank, so all replicas get bit-identical
-//           gradients; scales, rounds once, writes dW, advances the epoch in device memory (CUDA-graph
-//           capturable: no host argument changes between replays).
+//   push    (peer_push_kernel = the kernel that reduces the split-K partials of tc_wgrad_kernel, or reads
+//           an existing gradient): every CTA sums its 128-value slice in fp32 and writes it straight into
+//           this rank's exchange buffer [slot][element] -- the reduction's output IS the send buffer, no
+//           staging copy, nothing else on the critical path of the weight gradient.
+//   finish  (peer_finish_kernel, a few small CTAs): publishes -- one system-scope fence, then the epoch is
+//           stored into every rank's flag word for this source (world tiny release stores over NVLink);
+//           waits until every source's flag shows this epoch (acquire loads on its OWN flags); pulls the
+//           world's slices with TMA bulk copies through the peer mapping (its own locally) and sums them in
+//           rank order -- the same order on every rank, so all replicas get bit-identical gradients;
+//           scales, rounds once, writes dW, advances the epoch in device memory (CUDA-graph capturable: no
+//           host argument changes between replays).
 //
-// The caller puts independent work between the two (the input-gradient kernel of the same layer), so the
-// flags have long arrived when finish starts.  Two earlier versions, both correct, both measured at N = 2
-// against the NCCL hook (profiles/README.md, sessions n2b / n2c): (1) push + wait + sum in ONE kernel --
-// ~20 us of NVLink round trips on the critical path and 296 spinning CTAs beside the input-gradient
-// kernel: 0.169 vs 0.147 ms per config-2 step; (2) every CTA PUSHING its slice into every rank's buffer
-// with a fence.sys + remote arrival per CTA -- 864 system-scope fences made the reduction kernel 22 us
-// slower (86 vs 64 us weight gradient): 0.170 vs 0.146 ms.  Hence local writes, ONE system fence, and the
-// receiver pulling 0.44 MB per peer (a few us at NVLink 5 bandwidth).
+// The caller runs finish behind the input-gradient kernel of the same layer (on the forked stream of the
+// captured backward), off the critical path.  What was measured on the way here, all correct, all at N = 2
+// on config 2 against the NCCL hook at 0.146-0.147 ms per pipelined step (profiles/README.md, sessions n2b-n2m):
+//   (1) push + wait + sum in ONE kernel, every CTA storing into every rank's buffer: 0.169 ms;
+//   (2) the same split into push / finish: 0.170 ms -- 864 system-scope fences (one per CTA) made the
+//       weight-gradient region 22 us slower;
+//   (3) local writes, the last CTA of the reduction publishing, receivers pulling (LDG, then TMA bulk copies,
+//       16 then 64 CTAs, gpu- or system-scope fence, normal or high-priority stream): 0.163-0.168 ms, none of
+//       these knobs mattered;
+//   (4) what mattered: every dependent kernel on the stream that carries forward -> weight gradient costs ~8 us
+//       of launch + queueing when the next cloud's rulebook kernels share the GPU (a world-of-one group, no
+//       NVLink at all, showed the same +22 us), and the in-kernel publish (per-CTA fence + counter + the
+//       acknowledgement of the remote flag stores) another ~8 us.  With the receive side AND the publish
+//       behind the input gradient on the forked stream and no copy of dW afterwards the fused path reaches
+//       NCCL's time at N = 2.
 //
-// No grid-wide barrier, no host involvement.  publish never waits, so ranks cannot deadlock each other;
-// a peer that never shows up trips the group's timeout in finish (error word + NaN result) instead of
-// hanging the GPU.  Two slots alternate by epoch: rank r overwrites slot e&1 in its publish of epoch e+2,
-// which is stream-ordered after its finish of e+1, which needed every peer's flag of e+1, which that peer
-// stored after its own finish of e -- so nobody is still reading r's slot e&1.  Hence the contract: on
-// each rank publish and finish of one group alternate in stream order (one exchange in flight), same
-// sequence on all ranks.
+// No grid-wide barrier, no host involvement.  Neither kernel waits for a peer before it has published, so ranks
+// cannot deadlock each other; a peer that never shows up trips the group's timeout in finish (error word +
+// NaN result) instead of hanging the GPU.  Two slots alternate by epoch: rank r overwrites slot e&1 in its
+// push of epoch e+2, which is stream-ordered after its finish of e+1, which needed every peer's flag of e+1,
+// which that peer stored in its own finish of e+1, i.e. after its finish of e -- so nobody is still reading
+// r's slot e&1.  Hence the contract: on each rank push and finish of one group alternate in stream order (one
+// exchange in flight), same sequence on all ranks.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "peer.cuh"
@@ -78,7 +84,7 @@ constexpr int PX_THREADS = 256, PX_WARPS = PX_THREADS / 32;
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
 peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, const T *__restrict__ src, int64_t total,
-                 PeerPtrs peers, int world, int rank, int64_t capacity, int defer_signal) {
+                 PeerPtrs peers, int world, int rank, int64_t capacity, int publish) {
     __shared__ float4 acc_s[PX_WARPS][32];
     __shared__ unsigned s_epoch;
     PeerState *st = reinterpret_cast<PeerState *>(peers.buf[rank]);
@@ -117,7 +123,7 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     }
     if (i < total)                                         // the padded tail of the last float4 carries zeros
         *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.buf[rank] + PEER_DATA) + (int64_t)(epoch & 1u) * capacity + i) = t;
-    if (defer_signal & 1) return;                          // peer_signal_kernel publishes (A/B: debug bit 8192)
+    if (!(publish & 1)) return;                            // default: the finish kernel publishes (see there)
     __threadfence();
     __syncwarp();
     unsigned last = 0;
@@ -125,7 +131,7 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     // every slice of this rank is in its buffer (= visible in this GPU's L2, where the peers' reads arrive): tell everybody
-    if (defer_signal & 2) {                                // A/B (debug bit 16384): gpu-scope fence + plain system-scope flag store
+    if (publish & 2) {                                     // A/B (debug bit 16384): gpu-scope fence + plain system-scope flag store
         __threadfence();
         if (lane == 0) st->done = 0;
         if (lane < world)
@@ -135,15 +141,6 @@ peer_push_kernel(const float *__restrict__ partial, int64_t stride, int chunks, 
     __threadfence_system();
     if (lane == 0) st->done = 0;
     if (lane < world) st_release_sys(reinterpret_cast<unsigned *>(peers.buf[lane] + PEER_FLAGS) + rank, epoch + 1u);
-}
-
-// the publish step on its own (one warp): everything earlier in the stream is complete, make it visible
-// system-wide and store the epoch into every rank's flag word
-__global__ void peer_signal_kernel(PeerPtrs peers, int world, int rank) {
-    const unsigned epoch = reinterpret_cast<const PeerState *>(peers.buf[rank])->epoch;
-    __threadfence_system();
-    if ((int)threadIdx.x < world)
-        st_release_sys(reinterpret_cast<unsigned *>(peers.buf[threadIdx.x] + PEER_FLAGS) + rank, epoch + 1u);
 }
 
 // Receive side.  It runs BESIDE the persistent input-gradient kernel (whose CTAs own most of every SM's register
@@ -158,7 +155,7 @@ constexpr int FIN_MAX_CTAS = 64;               // 0.44 MB per peer = 54 chunks: 
 template <typename T>
 __global__ void __launch_bounds__(PX_THREADS)
 peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world, int rank, int64_t capacity, float scale,
-                   unsigned long long timeout_ns) {
+                   unsigned long long timeout_ns, int publish) {
     extern __shared__ __align__(128) uint8_t fin_smem[];      // [world][FIN_CHUNK_BYTES] + mbarrier
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned s_epoch;
@@ -168,6 +165,14 @@ peer_finish_kernel(T *__restrict__ dst, int64_t total, PeerPtrs peers, int world
     if (threadIdx.x == 0) { s_epoch = st->epoch; s_bad = 0; mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     const unsigned epoch = s_epoch, target = epoch + 1u;
+    if (publish && blockIdx.x == 0 && threadIdx.x < world) {
+        // This rank's slices were written by an EARLIER kernel of this stream (the weight-gradient reduction): they
+        // are complete and visible on this GPU.  One system-scope fence, then the epoch goes to every rank's flag
+        // word.  (Publishing from the reduction kernel itself -- last CTA out, debug bit 8192 -- put a per-CTA fence
+        // + counter and the NVLink store acknowledgement on the critical path: +8 us on the weight gradient.)
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned *>(peers.buf[threadIdx.x] + PEER_FLAGS) + rank, target);
+    }
     if (threadIdx.x < world) {
         const unsigned *flag = reinterpret_cast<const unsigned *>(mine + PEER_FLAGS) + threadIdx.x;
         const unsigned long long t0 = globaltimer_ns();
@@ -251,21 +256,14 @@ int peer_push(const float *partial, int64_t stride, int chunks, const void *src,
     const PeerPtrs pp = peer_ptrs(pg);
     const int64_t cap = (int64_t)(pg->capacity_bytes / 4);
     const unsigned grid = push_ctas(total);
-    const int defer = ((runtime_cfg().debug & 8192) ? 1 : 0) | ((runtime_cfg().debug & 16384) ? 2 : 0);
-#define PX_LAUNCH(T) peer_push_kernel<T><<<grid, PX_THREADS, 0, stream>>>(partial, stride, chunks, (const T *)src, total, pp, pg->world, pg->rank, cap, defer)
+    const int publish = ((runtime_cfg().debug & 8192) ? 1 : 0) | ((runtime_cfg().debug & 16384) ? 2 : 0);
+#define PX_LAUNCH(T) peer_push_kernel<T><<<grid, PX_THREADS, 0, stream>>>(partial, stride, chunks, (const T *)src, total, pp, pg->world, pg->rank, cap, publish)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
     else if (dtype == SPX_F32) PX_LAUNCH(float);
     else { set_error("peer push: dtype %d not supported", dtype); return 2; }
 #undef PX_LAUNCH
     SPX_CHECK_LAUNCH("peer_push_kernel");
-    return 0;
-}
-
-int peer_signal(const spx_peer_group *pg, cudaStream_t stream) {
-    if (int rc = check_group(pg, 0, "peer signal")) return rc;
-    peer_signal_kernel<<<1, 32, 0, stream>>>(peer_ptrs(pg), pg->world, pg->rank);
-    SPX_CHECK_LAUNCH("peer_signal_kernel");
     return 0;
 }
 
@@ -280,13 +278,14 @@ int peer_finish(void *dst, int64_t total, int dtype, const spx_peer_group *pg, f
     const unsigned grid = (unsigned)(nchunks < max_ctas ? nchunks : max_ctas);
     const size_t smem = (size_t)pg->world * FIN_CHUNK_BYTES;
     const unsigned long long timeout_ns = (unsigned long long)(pg->timeout_ms > 0 ? pg->timeout_ms : 20000) * 1000000ull;
+    const int publish = (runtime_cfg().debug & 8192) ? 0 : 1;          // bit 8192: the reduction kernel has published
 #define PX_LAUNCH(T)                                                                                                  \
     do {                                                                                                              \
         auto fn = peer_finish_kernel<T>;                                                                              \
         if (smem > 48 * 1024 && !func_configured((const void *)fn, current_device()))                                 \
             SPX_CHECK_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                                 SPX_MAX_PEERS * FIN_CHUNK_BYTES));                                    \
-        fn<<<grid, PX_THREADS, smem, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, timeout_ns);     \
+        fn<<<grid, PX_THREADS, smem, stream>>>((T *)dst, total, pp, pg->world, pg->rank, cap, scale, timeout_ns, publish);      \
     } while (0)
     if (dtype == SPX_F16) PX_LAUNCH(__half);
     else if (dtype == SPX_BF16) PX_LAUNCH(__nv_bfloat16);
@@ -359,12 +358,6 @@ extern "C" int spx_peer_push(const spx_peer_group *pg, const void *data, int64_t
     return peer_push(nullptr, 0, 0, data, count, dtype, pg, (cudaStream_t)stream);
 }
 
-/* only with spx_debug_configure bit 8192 (the reduction kernel does not publish): publish what has been
- * pushed on this stream so far */
-extern "C" int spx_peer_signal(const spx_peer_group *pg, spx_stream_t stream) {
-    return peer_signal(pg, (cudaStream_t)stream);
-}
-
 extern "C" int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t count, int dtype, float scale,
                                spx_stream_t stream) {
     SPX_REQUIRE(out != nullptr || count == 0, "peer_finish: out is NULL");
@@ -374,6 +367,5 @@ extern "C" int spx_peer_finish(const spx_peer_group *pg, void *out, int64_t coun
 extern "C" int spx_peer_allreduce(const spx_peer_group *pg, void *data, int64_t count, int dtype, float scale,
                                   spx_stream_t stream) {
     if (int rc = spx_peer_push(pg, data, count, dtype, stream)) return rc;
-    if (runtime_cfg().debug & 8192) if (int rc = spx_peer_signal(pg, stream)) return rc;
     return spx_peer_finish(pg, data, count, dtype, scale, stream);
 }

@@ -121,7 +121,6 @@ class PeerGroup:
         assert self.world <= _cabi.SPX_MAX_PEERS, f"at most {_cabi.SPX_MAX_PEERS} ranks"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.scale = 1.0 / self.world if average else 1.0
-        self.defer_signal = False        # A/B: publish from a separate one-warp kernel (needs debug bit 8192)
         self._lib = lib
         self._mapped: List[int] = []
         with torch.cuda.device(self.device):
@@ -167,7 +166,6 @@ class PeerGroup:
         for r in range(world):
             pg = object.__new__(cls)
             pg.world, pg.rank, pg.scale = world, r, (1.0 / world if average else 1.0)
-            pg.defer_signal = False
             pg.device = torch.device("cuda", torch.cuda.current_device())
             pg._lib, pg._mapped, pg._own = lib, [], bufs[r]
             g = _cabi.PeerGroup()

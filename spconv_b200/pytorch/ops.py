@@ -654,8 +654,6 @@ def implicit_gemm_backward(features: torch.Tensor, filters: torch.Tensor, out_bp
         if _PEER_TRIAGE & 1:
             return
         with timer.record("implicit_gemm_wgrad_exchange", _stream()):
-            if _PEERS.defer_signal:
-                _cabi.check(lib.spx_peer_signal(ctypes.byref(_PEERS.group), _stream()), "peer_signal")
             _cabi.check(lib.spx_peer_finish(ctypes.byref(_PEERS.group), _ptr(dfilters), dfilters.numel(),
                                             _DTYPE_CODE[dfilters.dtype], _PEERS.scale, _stream()), "peer_finish")
 

@@ -73,17 +73,15 @@ def test_world_of_one_equals_the_plain_weight_gradient(cuda_dev, no_peers):
     pg.close()
 
 
-@pytest.mark.parametrize("world,defer", [(2, False), (3, False), (2, True)], ids=["2", "3", "2-separate-publish"])
+@pytest.mark.parametrize("world,defer", [(2, False), (3, False), (2, True)], ids=["2", "3", "2-publish-in-reduction"])
 def test_ranks_on_one_gpu_exchange_through_the_fused_kernel(world, defer, cuda_dev, no_peers):
     """world ranks = world streams: every rank's reduction kernel publishes its slices, every finish pulls them all.
-    defer: the A/B variant where a one-warp kernel publishes (spx_debug_configure bit 8192)."""
+    defer: the A/B variant where the reduction kernel's last CTA publishes (spx_debug_configure bit 8192)."""
     from spconv_b200 import _cabi
     from spconv_b200.pytorch import ops
     from spconv_b200.pytorch.dist import PeerGroup
     ring = PeerGroup.local_ring(world, capacity_bytes=1 << 20, average=True)
     _cabi.check(_cabi.load().spx_debug_configure(-1, 0, 8192 if defer else 0, None, 0), "debug_configure")
-    for pg in ring:
-        pg.defer_signal = defer
     streams = [torch.cuda.Stream() for _ in range(world)]
     cases = [(64, 64, True, torch.float16), (64, 128, False, torch.bfloat16), (32, 32, True, torch.float16),
              (48, 24, True, torch.float16), (64, 64, True, torch.float16)]       # K=24: FMA kernel + standalone exchange
