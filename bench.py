@@ -86,8 +86,11 @@ def parse_args():
                          "3 = 2 + the eager encoder prefetches its whole rulebook chain from a worker thread")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
-    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl", "fused-local"],
-                    help="N > 1: dW all-reduce fused into the weight-gradient kernel over NVLink peer memory, or NCCL")
+    ap.add_argument("--allreduce", default="nccl", choices=["fused", "nccl", "fused-local"],
+                    help="N > 1: NCCL all-reduce of dW from a hook right behind the weight gradient (default: measured "
+                         "faster under graph replay, 0.146 vs 0.159 ms per step at N = 2), or the exchange over NVLink peer "
+                         "memory whose send side is the weight-gradient reduction kernel (csrc/peer.cu; faster through the "
+                         "eager module API); fused-local = triage (every rank exchanges with itself)")
     ap.add_argument("--peer-triage", type=int, default=0, help="triage of the fused exchange: 1 skip finish, 2 plain "
                     "weight gradient + finish only, 4 finish on the launching stream")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")

@@ -25,12 +25,15 @@
 //   (3) local writes, the last CTA of the reduction publishing, receivers pulling (LDG, then TMA bulk copies,
 //       16 then 64 CTAs, gpu- or system-scope fence, normal or high-priority stream): 0.163-0.168 ms, none of
 //       these knobs mattered;
-//   (4) what mattered: every dependent kernel on the stream that carries forward -> weight gradient costs ~8 us
-//       of launch + queueing when the next cloud's rulebook kernels share the GPU (a world-of-one group, no
-//       NVLink at all, showed the same +22 us), and the in-kernel publish (per-CTA fence + counter + the
-//       acknowledgement of the remote flag stores) another ~8 us.  With the receive side AND the publish
-//       behind the input gradient on the forked stream and no copy of dW afterwards the fused path reaches
-//       NCCL's time at N = 2.
+//   (4) a world-of-one group (no NVLink at all) shows the same +20 us over the single-GPU graph: the cost is the
+//       shape of the captured backward, not the wire.  Every dependent kernel behind forward -> weight gradient
+//       costs launch + queueing time when the next cloud's rulebook kernels share the GPU, and the in-kernel
+//       publish (per-CTA fence + counter + acknowledgement of the remote flag stores) ~8 us more.  With publish
+//       and receive side behind the input gradient on the forked stream and no copy of dW afterwards: 0.159 ms --
+//       still 13 us behind the NCCL hook under graph replay, ahead of it through the eager module API (0.60 vs
+//       0.65 ms per config-2 step, 1.57-1.74 vs 1.65-1.90 ms per 6-layer encoder step): one native call per
+//       layer instead of a collective launch.  bench.py therefore defaults to the NCCL hook for the graph-replayed
+//       headline and keeps this path selectable (--allreduce fused).
 //
 // No grid-wide barrier, no host involvement.  Neither kernel waits for a peer before it has published, so ranks
 // cannot deadlock each other; a peer that never shows up trips the group's timeout in finish (error word +
