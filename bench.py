@@ -86,11 +86,13 @@ def parse_args():
                          "3 = 2 + the eager encoder prefetches its whole rulebook chain from a worker thread")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE configs (default: only in the default-workload run)")
-    ap.add_argument("--allreduce", default="nccl", choices=["fused", "nccl", "fused-local"],
-                    help="N > 1: NCCL all-reduce of dW from a hook right behind the weight gradient (default: measured "
-                         "faster under graph replay, 0.146 vs 0.159 ms per step at N = 2), or the exchange over NVLink peer "
-                         "memory whose send side is the weight-gradient reduction kernel (csrc/peer.cu; faster through the "
-                         "eager module API); fused-local = triage (every rank exchanges with itself)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "fused", "nccl", "fused-local"],
+                    help="N > 1, the all-reduce of dW: nccl = from a hook right behind the weight gradient; fused = the "
+                         "exchange over NVLink peer memory whose send side is the weight-gradient reduction kernel "
+                         "(csrc/peer.cu); auto (default) = what was measured faster under graph replay: nccl up to 4 GPUs "
+                         "(0.146 vs 0.159 ms per step at N = 2), fused from 8 (0.1661 vs 0.1686 ms; through the eager module "
+                         "API fused wins everywhere: 1.4 vs 4.2 ms at N = 8); fused-local = triage (every rank exchanges "
+                         "with itself)")
     ap.add_argument("--peer-triage", type=int, default=0, help="triage of the fused exchange: 1 skip finish, 2 plain "
                     "weight gradient + finish only, 4 finish on the launching stream")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
@@ -258,6 +260,8 @@ class Ctx:
             # without the cross-rank dependency
             from spconv_b200.pytorch.dist import PeerGroup
             self.peers = PeerGroup.local_ring(1, capacity_bytes=8 << 20, average=False)[0]
+        if args.allreduce == "auto":
+            args.allreduce = "fused" if self.world >= 8 else "nccl"
         if self.world > 1 and args.allreduce == "fused":
             from spconv_b200.pytorch.dist import PeerGroup
             ok = torch.ones(1, device=self.dev, dtype=torch.int32)
