@@ -10,7 +10,7 @@ copy, it can run ahead of the step that consumes it:
     y = model(pre.ready(x_next))                    # the layers find their rulebooks through indice_key
 
 Why it pays: (i) rulebook kernels are latency-bound integer work, the GEMM kernels are LSU / L2-bound --
-side by side they overlap (bench.py: 0.18 -> 0.135 ms per config-2 step); (ii) a strided conv reads its
+off the critical path they cost nothing but SM time (bench.py: 0.18 -> 0.135-0.14 ms per config-2 step); (ii) a strided conv reads its
 output count back to the host (``spx_conv_rulebook_stage1``, as the reference does,
 ``spconv/csrc/sparse/indices.py:1454-1455``) -- on the training stream that read-back drains the whole
 GEMM queue three times per SECOND-encoder step; on the prefetch stream it only waits for the rulebook
