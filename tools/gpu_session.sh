@@ -5,8 +5,7 @@ TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 echo "== session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -400) > $O/${TAG}_tests.log
+(timeout 170 python -m pytest tests -m gpu -q -x 2>&1 | tail -400) > $O/${TAG}_tests.log
 tail -6 $O/${TAG}_tests.log | cut -c1-300
-(timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
-(timeout 200 python tools/ab_conv_rulebook.py > $O/${TAG}_ab_conv_rulebook.log 2>&1); cat $O/${TAG}_ab_conv_rulebook.log | tail -8
+(timeout 200 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
 echo "== done $(date -u +%H:%M:%S)"
