@@ -8,4 +8,5 @@ echo "== session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.
 (timeout 170 python -m pytest tests -m gpu -q -x 2>&1 | tail -400) > $O/${TAG}_tests.log
 tail -6 $O/${TAG}_tests.log | cut -c1-300
 (timeout 200 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err); tail -c 300 $O/${TAG}_bench.err; head -c 400 $O/${TAG}_bench.json; echo
+(timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke OK')" 2>&1 | tail -2)
 echo "== done $(date -u +%H:%M:%S)"
