@@ -877,9 +877,12 @@ def measure(w: Workload, ctx: Ctx, steps: int, warmup: int, headline: bool) -> d
     ms_value = sorted(runs)[1]
     ms_serial = float(np.mean(ctx.timed_loop(serial_step, steps))) if pipe is not None else None
     ms_e2e = float(np.mean(ctx.timed_loop(e2e_step, steps)))
-    ms_e2e_naive = float(np.mean(ctx.timed_loop(e2e_step_eager, steps)))
-    ms_e2e_eager = float(np.mean(ctx.timed_loop(e2e_step_eager_pipe, steps)))
     clocks = sampler.stop() if (ctx.rank == 0 and headline) else {}
+    # The eager legs are host-bound: 20 steps are ~12 ms of wall clock, one scheduling hiccup (or the clock sampler
+    # forking nvidia-smi, hence stopped above: it covers the device-timed legs) doubles the mean.  Median of three
+    # repetitions, as for `value`.
+    ms_e2e_naive = sorted(float(np.mean(ctx.timed_loop(e2e_step_eager, steps))) for _ in range(3))[1]
+    ms_e2e_eager = sorted(float(np.mean(ctx.timed_loop(e2e_step_eager_pipe, steps))) for _ in range(3))[1]
 
     # indice_key-reuse leg (configs[3]): one rulebook, two layers
     ms_reuse = None
