@@ -84,3 +84,56 @@ def test_tile_table_elems_formula_matches_the_library():
         for kv in (1, 8, 27, 81, 128):
             tiles = max((rows + 127) // 128, 1)
             assert lib.spx_tile_table_elems(rows, kv) == tiles * (kv + 1) * 128 + tiles * 8 + 64
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """the three structs that cross the boundary have the same size and field offsets in ctypes as in C
+    (include/spconv_b200.h compiled by gcc) -- a silent mismatch would shift every pointer argument"""
+    import ctypes
+    import subprocess
+    from spconv_b200 import _cabi
+    structs = {"spx_conv_geometry": _cabi.ConvGeometry, "spx_gemm_desc": _cabi.GemmDesc, "spx_peer_group": _cabi.PeerGroup}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "spconv_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln.strip():
+            continue
+        cname, field, val = ln.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == want, f"{cname}.{field}: C {val} vs ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_peer_exchange_host_side_validation(lib):
+    """spx_peer_* argument checks and sizes run without a GPU (no buffer is created here)"""
+    import ctypes
+    from spconv_b200 import _cabi
+    assert _cabi.SPX_MAX_PEERS == 16
+    # two epochs of this rank's own fp32 slices + the 4 KB header (state, flags)
+    assert lib.spx_peer_buffer_bytes(1 << 20, 8) == 4096 + 2 * (1 << 20)
+    assert lib.spx_peer_buffer_bytes(1 << 20, 0) == 0 and lib.spx_peer_buffer_bytes(1 << 20, 17) == 0
+    g = _cabi.PeerGroup()
+    g.world, g.rank, g.capacity_bytes = 2, 5, 1 << 20
+    assert lib.spx_peer_push(ctypes.byref(g), 1, 16, _cabi.SPX_F32, None) != 0
+    assert "bad peer group" in _cabi.last_error()
+    g.rank = 1
+    assert lib.spx_peer_finish(ctypes.byref(g), 1, (1 << 20), _cabi.SPX_F32, 1.0, None) != 0
+    assert "exceed the exchange capacity" in _cabi.last_error()
+    assert lib.spx_peer_push(ctypes.byref(g), 1, 16, _cabi.SPX_F32, None) != 0
+    assert "buffer of rank 0 is NULL" in _cabi.last_error()
+    d = _cabi.GemmDesc()
+    d.kv, d.c_in, d.c_out, d.dtype, d.n_in, d.n_out = 27, 16, 16, _cabi.SPX_F16, 10, 10
+    assert lib.spx_implicit_gemm_wgrad_push(ctypes.byref(d), 1, 1, 1, None, 0, None, None) != 0
+    assert "peer group is NULL" in _cabi.last_error()

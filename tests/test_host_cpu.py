@@ -160,3 +160,25 @@ def test_fuse_bn_weights_equals_dense_conv_then_bn():
         * torch.rsqrt(bn.running_var + bn.eps).view(1, -1, 1, 1, 1)
     got2 = torch.nn.functional.conv3d(x, wf2.detach().permute(0, 4, 1, 2, 3), bf2.detach())
     assert (ref2 - got2).abs().max() < 1e-5
+
+
+def test_prefetchable_chain_follows_module_order_and_stops_where_it_cannot():
+    """RulebookPrefetcher's layer discovery (host logic, no device): keyed layers in application order, strided ones
+    included; a layer without indice_key, with the Native algo, or an inverse conv ends the chain"""
+    import spconv_b200.pytorch as spconv
+    from spconv_b200.core import ConvAlgo
+    from spconv_b200.pytorch.prefetch import input_level_subm_layers, prefetchable_chain
+    net = spconv.SparseSequential(
+        spconv.SubMConv3d(4, 8, 3, indice_key="a"), spconv.SubMConv3d(8, 8, 3, indice_key="a"),
+        spconv.SparseConv3d(8, 16, 3, 2, 1, indice_key="d1"), spconv.SubMConv3d(16, 16, 3, indice_key="b"),
+        spconv.SubMConv3d(16, 16, 1, indice_key="b"),               # 1x1: no rulebook, skipped
+        spconv.SparseConv3d(16, 16, 3, 2, 1),                        # no key: the chain ends here
+        spconv.SubMConv3d(16, 16, 3, indice_key="c"))
+    assert [m.indice_key for m in prefetchable_chain(net)] == ["a", "a", "d1", "b"]
+    assert [m.indice_key for m in input_level_subm_layers(net)] == ["a"]
+    native = [spconv.SubMConv3d(4, 4, 3, indice_key="n", algo=ConvAlgo.Native), spconv.SubMConv3d(4, 4, 3, indice_key="m")]
+    assert prefetchable_chain(native) == []
+    inv = [spconv.SparseConv3d(4, 4, 3, 2, 1, indice_key="d"), spconv.SparseInverseConv3d(4, 4, 3, indice_key="d")]
+    assert [m.indice_key for m in prefetchable_chain(inv)] == ["d"]
+    pre = spconv.RulebookPrefetcher(net)                              # construction needs no device
+    assert len(pre.layers) == 4 and pre.stream is None
