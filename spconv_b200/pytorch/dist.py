@@ -123,32 +123,52 @@ class PeerGroup:
         self.scale = 1.0 / self.world if average else 1.0
         self._lib = lib
         self._mapped: List[int] = []
+        self._own = None
+        self.group = _cabi.PeerGroup()
+        failure: Optional[str] = None
+        # Every rank takes part in every collective of this constructor exactly once, whatever fails locally: a rank
+        # that cannot create or map a buffer must not leave the others waiting in a collective it never joins.
         with torch.cuda.device(self.device):
-            own = ctypes.c_void_p()
             handle = (ctypes.c_ubyte * 64)()
-            _cabi.check(lib.spx_peer_buffer_create(capacity_bytes, self.world, ctypes.byref(own), handle),
-                        "peer_buffer_create")
-            self._own = own.value
+            try:
+                own = ctypes.c_void_p()
+                _cabi.check(lib.spx_peer_buffer_create(capacity_bytes, self.world, ctypes.byref(own), handle),
+                            "peer_buffer_create")
+                self._own = own.value
+            except Exception as e:                       # noqa: BLE001 -- reported through the consensus below
+                failure = f"{type(e).__name__}: {e}"
             handles: List[Optional[bytes]] = [None] * self.world
             if self.world > 1:
-                dist.all_gather_object(handles, bytes(handle), group=group)
+                dist.all_gather_object(handles, bytes(handle) if failure is None else None, group=group)
             else:
-                handles[0] = bytes(handle)
-            g = _cabi.PeerGroup()
+                handles[0] = bytes(handle) if failure is None else None
+            g = self.group
             g.world, g.rank, g.timeout_ms, g.capacity_bytes = self.world, self.rank, timeout_ms, capacity_bytes
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    g.buffers[r] = self._own
-                    continue
-                mapped = ctypes.c_void_p()
-                raw = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                _cabi.check(lib.spx_peer_buffer_open(raw, ctypes.byref(mapped)), f"peer_buffer_open(rank {r})")
-                self._mapped.append(mapped.value)
-                g.buffers[r] = mapped.value
-            self.group = g
+            if failure is None and any(h is None for h in handles):
+                failure = "a peer could not create its exchange buffer"
+            if failure is None:
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            g.buffers[r] = self._own
+                            continue
+                        mapped = ctypes.c_void_p()
+                        raw = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                        _cabi.check(lib.spx_peer_buffer_open(raw, ctypes.byref(mapped)), f"peer_buffer_open(rank {r})")
+                        self._mapped.append(mapped.value)
+                        g.buffers[r] = mapped.value
+                except Exception as e:                   # noqa: BLE001
+                    failure = f"{type(e).__name__}: {e}"
             torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier(group=group)               # nobody pushes before every buffer is mapped and zeroed
+            if self.world > 1:
+                # consensus (also the barrier: nobody pushes before every buffer is mapped and zeroed)
+                ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0 and failure is None:
+                    failure = "a peer could not map the exchange buffers"
+        if failure is not None:
+            self.close()
+            raise RuntimeError(f"PeerGroup: peer-memory exchange unavailable on rank {self.rank}: {failure}")
 
     @classmethod
     def local_ring(cls, world: int, capacity_bytes: int = 8 << 20, average: bool = True,
