@@ -93,8 +93,8 @@ def parse_args():
                          "(0.146 vs 0.159 ms per step at N = 2), fused from 8 (0.1661 vs 0.1686 ms; through the eager module "
                          "API fused wins everywhere: 1.4 vs 4.2 ms at N = 8); fused-local = triage (every rank exchanges "
                          "with itself)")
-    ap.add_argument("--peer-triage", type=int, default=0, help="triage of the fused exchange: 1 skip finish, 2 plain "
-                    "weight gradient + finish only, 4 finish on the launching stream")
+    ap.add_argument("--peer-triage", type=int, default=0, help="triage of the fused exchange (timing only, results are wrong): "
+                    "1 skip finish, 2 plain weight gradient instead of push")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="voxels in the CPU-baseline sample")
     ap.add_argument("--debug-bits", type=int, default=0,
                     help="spx_debug_configure bits for A/B runs (64 onesweep sort, 128 round-1 conv rulebook, "
