@@ -64,13 +64,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *addr) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
     return v;
 }
-// system-scope load of a slice that another GPU wrote: must not be served from a stale cached line (the two
-// slots are rewritten every other epoch)
-__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float *addr) {
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
