@@ -41,7 +41,8 @@
 // push of epoch e+2, which is stream-ordered after its finish of e+1, which needed every peer's flag of e+1,
 // which that peer stored in its own finish of e+1, i.e. after its finish of e -- so nobody is still reading
 // r's slot e&1.  Hence the contract: on each rank push and finish of one group alternate in stream order (one
-// exchange in flight), same sequence on all ranks.
+// exchange in flight), same sequence on all ranks.  tests/test_peer_protocol_cpu.py explores every interleaving of this
+// state machine for 2-4 ranks (and shows that one slot, or a publish before the data, is caught).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "peer.cuh"
